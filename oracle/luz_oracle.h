@@ -1,0 +1,108 @@
+/*
+ * luz_oracle.h -- C interface of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * The oracle restates, in scalar fp32 C++ built with -ffp-contract=off, the arithmetic of the
+ * reference's lighting path: source/Shaders/light.frag, taa.comp, utils.glsl, present.frag
+ * and (as an input producer) opaque.vert/frag, plus the any-hit ray-query semantics the
+ * Vulkan driver supplies.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load it.  libluzrt.so never does.
+ *
+ * PARITY PINNING: the reference ships no tests, golden images or known-answer vectors for this
+ * path and its GLSL cannot be executed in this environment (no Vulkan loader / glslang /
+ * lavapipe), so the shader restatement is "parity unpinned" against reference *outputs*; it is
+ * pinned only by hand-derived known answers (tests/test_oracle_kat.py) and by the reference's
+ * own compiled host code for everything host-side (oracle/ref_dump.cpp -> tests/golden).
+ */
+#ifndef LUZ_ORACLE_H
+#define LUZ_ORACLE_H
+
+#include <stdint.h>
+#include "../include/luz_wire.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_mesh {
+    const void* vertices;   /* vertex_stride bytes each, position = first 12 bytes */
+    uint32_t vertex_count;
+    uint32_t vertex_stride;
+    const uint32_t* indices;
+    uint32_t index_count;
+} orc_mesh;
+
+typedef struct orc_instance {
+    uint32_t mesh;          /* index into the mesh array */
+    float model_mat[16];    /* column-major glm::mat4 */
+    uint32_t custom_index;  /* index into ModelBlock[] */
+} orc_instance;
+
+typedef struct orc_texture {
+    const uint8_t* rgba8;
+    uint32_t width, height;
+} orc_texture;
+
+typedef struct orc_gbuffer {
+    uint8_t* albedo;   /* RGBA8   */
+    float* normal;     /* RGBA32F */
+    uint8_t* material; /* RGBA8   */
+    uint8_t* emission; /* RGBA8   */
+    float* depth;      /* F32     */
+} orc_gbuffer;
+
+typedef struct orc_stats {
+    uint64_t lit_pixels;
+    uint64_t rays;
+    uint64_t rays_occluded;
+} orc_stats;
+
+typedef struct orc_world orc_world;
+
+/* Builds per-mesh BVH2s and a BVH2 over instances (used only when exhaustive == 0). */
+orc_world* orc_world_create(const orc_mesh* meshes, uint32_t n_meshes, const orc_instance* instances,
+                            uint32_t n_instances);
+void orc_world_destroy(orc_world* w);
+void orc_set_threads(int n); /* 0 = all cores */
+int orc_get_threads(void);
+
+/* Any-hit over n rays: hit[i] = 1 if some triangle is hit with tmin < t < tmax.
+ * exhaustive != 0: every triangle of every instance is tested (truth); else BVH2 traversal. */
+void orc_trace_any(const orc_world* w, uint32_t n, const float* origins3, const float* dirs3, const float* tmin,
+                   const float* tmax, int exhaustive, uint8_t* hit);
+/* Closest hit: t[i] (inf if none), inst[i], prim[i]. */
+void orc_trace_closest(const orc_world* w, uint32_t n, const float* origins3, const float* dirs3, const float* tmin,
+                       const float* tmax, int exhaustive, float* t, int32_t* inst, int32_t* prim);
+
+/* light.frag main() over rows [y0, y1).  out_rgba32f is the full W*H*4 image (only the rows
+ * are written).  Masks may be NULL.  Returns 0, or -1 for the out-of-scope shadow-map branch. */
+int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                   uint32_t width, uint32_t height, const orc_gbuffer* gb, uint32_t frame,
+                   const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
+                   int exhaustive, uint32_t y0, uint32_t y1, float* out_rgba32f, uint32_t* shadow_mask,
+                   uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words, orc_stats* stats);
+
+/* taa.comp main() over rows [y0, y1). */
+int orc_taa_pass(const luzw_scene_block* scene, uint32_t width, uint32_t height, const float* light_in,
+                 const float* history, const float* depth, int reconstruct, uint32_t y0, uint32_t y1,
+                 float* out_rgba32f);
+
+/* present.frag imageType 0 -> BGRA8. */
+int orc_compose_pass(uint32_t width, uint32_t height, const float* light_in, uint8_t* out_bgra8);
+
+/* opaque.vert/frag as primary visibility (input producer). */
+int orc_gbuffer_pass(const luzw_scene_block* scene, const orc_world* world, const luzw_model_block* models,
+                     uint32_t n_models, const orc_texture* textures, uint32_t n_textures, uint32_t width,
+                     uint32_t height, int exhaustive, orc_gbuffer* out);
+
+/* Small exported helpers for known-answer tests. */
+void orc_blue_noise_sample(const uint8_t* bn, uint32_t bn_w, uint32_t bn_h, uint32_t px, uint32_t py, int i,
+                           uint32_t frame, float out2[2]);
+void orc_depth_to_world(const luzw_scene_block* scene, float u, float v, float depth, float out3[3]);
+float orc_mitchell(float x);
+int orc_tri_test(const float* v0, const float* v1, const float* v2, const float* org, const float* dir, float tmin,
+                 float tmax, float* t_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
