@@ -1,0 +1,879 @@
+// api.cu -- the C ABI of libluzrt.so (include/luzrt.h): context, resources and the frame calls.
+// Every entry point cites the reference call it replaces in luzrt.h; nothing here computes on the
+// CPU beyond marshalling (there is no CPU fallback by design).
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh.h"
+#include "passes.h"
+#include "traverse.cuh"
+
+using namespace luz;
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (lib) return true;
+        // RTLD_NOLOAD first: share the copy a host process (e.g. torch) already mapped
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+        if (!lib) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+    }
+};
+NcclApi g_nccl;
+
+struct Blas {
+    bool alive = false;
+    WideBvh bvh;
+    WideTri* tris = nullptr;
+    uint8_t* verts = nullptr;
+    uint32_t* indices = nullptr;
+    uint32_t stride = 0, n_verts = 0, n_tris = 0;
+    BoxF bounds{};
+    uint32_t levels = 0;
+};
+
+struct Texture {
+    uchar4* data = nullptr;
+    uint2 size{0, 0};
+};
+
+enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_COUNT };
+
+} // namespace
+
+struct luzrt_ctx {
+    int device = 0, rank = 0, world = 1;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    uint32_t debug = 0;
+
+    uint32_t w = 0, h = 0, y0 = 0, y1 = 0;
+    uchar4 *albedo = nullptr, *material = nullptr, *emission = nullptr, *compose = nullptr;
+    float4 *normal = nullptr, *lightA = nullptr, *lightB = nullptr, *lightHist = nullptr;
+    float* depth = nullptr;
+    bool history_valid = false;
+
+    uchar4* blue_noise = nullptr;
+    uint32_t bn_w = 0, bn_h = 0;
+
+    bool have_scene = false;
+    FrameConst fc{};
+    LightRec* d_lights = nullptr;
+    size_t lights_cap = 0;
+    uint32_t rays_per_lit_pixel = 0, shadow_bits = 0;
+
+    std::vector<Blas> blas;
+    BuildScratch scratch;
+    BoxF* d_boxes = nullptr; // triangle / instance boxes (grow-only)
+    size_t boxes_cap = 0;
+    BlasAttr* d_blas_attr = nullptr;
+    size_t blas_attr_cap = 0;
+    bool blas_attr_dirty = true;
+
+    WideBvh tlas;
+    bool have_tlas = false;
+    InstanceIn* d_inst_in = nullptr;
+    InstanceRec *d_recs_in = nullptr, *d_recs = nullptr;
+    InstanceMeta *d_meta_in = nullptr, *d_meta = nullptr;
+    size_t inst_cap = 0;
+    uint32_t n_inst = 0;
+    std::vector<luzrt_blas> last_blas;
+    std::vector<InstanceIn> host_inst;
+
+    std::vector<Texture> textures;
+    const uchar4** d_tex_data = nullptr;
+    uint2* d_tex_size = nullptr;
+    size_t tex_cap = 0;
+    bool tex_dirty = true;
+    luzw_model_block* d_models = nullptr;
+    size_t models_cap = 0;
+
+    uint32_t *d_shadow_mask = nullptr, *d_ao_mask = nullptr;
+    size_t shadow_mask_words = 0, ao_mask_words = 0; // per pixel
+    size_t shadow_mask_cap = 0, ao_mask_cap = 0;
+    DeviceStats* d_stats = nullptr;
+    unsigned long long* d_lit = nullptr;
+
+    cudaEvent_t ev[EV_COUNT][2]{};
+    bool ev_valid[EV_COUNT]{};
+
+    ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+int fail(luzrt_ctx* c, int code, const char* fmt, ...) {
+    if (c) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(c, expr)                                                                                         \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(c, _e == cudaErrorMemoryAllocation ? LUZRT_E_NOMEM : LUZRT_E_CUDA, "%s: %s", #expr, \
+                        cudaGetErrorString(_e));                                                            \
+    } while (0)
+
+#define REQUIRE(c, cond, msg) \
+    do {                      \
+        if (!(cond)) return fail(c, LUZRT_E_INVALID, "%s", msg); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <class T>
+int grow(luzrt_ctx* c, T*& p, size_t& cap, size_t need) {
+    if (cap >= need) return LUZRT_OK;
+    if (p) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaFree(p));
+        p = nullptr;
+        cap = 0;
+    }
+    const size_t n = need + need / 2;
+    CU(c, cudaMalloc(&p, n * sizeof(T)));
+    cap = n;
+    return LUZRT_OK;
+}
+
+void ev_begin(luzrt_ctx* c, int which) { cudaEventRecord(c->ev[which][0], c->stream); }
+void ev_end(luzrt_ctx* c, int which) {
+    cudaEventRecord(c->ev[which][1], c->stream);
+    c->ev_valid[which] = true;
+}
+
+void free_images(luzrt_ctx* c) {
+    void* ptrs[] = {c->albedo, c->material, c->emission, c->compose, c->normal, c->lightA, c->lightB, c->lightHist,
+                    c->depth};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    c->albedo = c->material = c->emission = c->compose = nullptr;
+    c->normal = c->lightA = c->lightB = c->lightHist = nullptr;
+    c->depth = nullptr;
+}
+
+void free_blas(Blas& b) {
+    free_wide_bvh(b.bvh);
+    if (b.tris) cudaFree(b.tris);
+    if (b.verts) cudaFree(b.verts);
+    if (b.indices) cudaFree(b.indices);
+    b = Blas();
+}
+
+void* image_ptr(luzrt_ctx* c, int which, size_t* bytes) {
+    const size_t px = (size_t)c->w * c->h;
+    switch (which) {
+        case LUZRT_IMG_LIGHT: *bytes = px * 16; return c->lightA;
+        case LUZRT_IMG_HISTORY: *bytes = px * 16; return c->lightHist;
+        case LUZRT_SHADOW_MASK: *bytes = px * c->shadow_mask_words * 4; return c->d_shadow_mask;
+        case LUZRT_AO_MASK: *bytes = px * c->ao_mask_words * 4; return c->d_ao_mask;
+        case LUZRT_GBUF_ALBEDO: *bytes = px * 4; return c->albedo;
+        case LUZRT_GBUF_NORMAL: *bytes = px * 16; return c->normal;
+        case LUZRT_GBUF_MATERIAL: *bytes = px * 4; return c->material;
+        case LUZRT_GBUF_EMISSION: *bytes = px * 4; return c->emission;
+        case LUZRT_GBUF_DEPTH: *bytes = px * 4; return c->depth;
+        case LUZRT_IMG_COMPOSE: *bytes = px * 4; return c->compose;
+        default: *bytes = 0; return nullptr;
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+const char* luzrt_version(void) { return "luzrt 0.1 (sm_100a)"; }
+
+int luzrt_create(int device_id, int rank, int world, luzrt_ctx** out) {
+    if (!out) return LUZRT_E_INVALID;
+    *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return LUZRT_E_INVALID;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device_id < 0 || device_id >= n) return LUZRT_E_NODEVICE;
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return LUZRT_E_NODEVICE;
+    if (prop.major != 10) return LUZRT_E_NODEVICE; // the kernels are sm_100a SASS only
+    if (cudaSetDevice(device_id) != cudaSuccess) return LUZRT_E_NODEVICE;
+    luzrt_ctx* c = new luzrt_ctx();
+    c->device = device_id;
+    c->rank = rank;
+    c->world = world;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return LUZRT_E_CUDA;
+    }
+    for (int i = 0; i < EV_COUNT; i++)
+        for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev[i][k]);
+    if (cudaMalloc(&c->d_stats, sizeof(DeviceStats)) != cudaSuccess ||
+        cudaMalloc(&c->d_lit, 64 * 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        luzrt_destroy(c);
+        return LUZRT_E_NOMEM;
+    }
+    cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream);
+    cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream);
+    c->blas.emplace_back(); // handle 0 is invalid
+    *out = c;
+    return LUZRT_OK;
+}
+
+void luzrt_destroy(luzrt_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    free_images(c);
+    for (auto& b : c->blas) free_blas(b);
+    free_wide_bvh(c->tlas);
+    for (auto& t : c->textures)
+        if (t.data) cudaFree(t.data);
+    void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
+                    c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models,
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (int i = 0; i < EV_COUNT; i++)
+        for (int k = 0; k < 2; k++)
+            if (c->ev[i][k]) cudaEventDestroy(c->ev[i][k]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* luzrt_last_error(luzrt_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int luzrt_comm_unique_id(void* out128) {
+    if (!out128) return LUZRT_E_INVALID;
+    if (!g_nccl.load()) return LUZRT_E_COMM;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return LUZRT_E_COMM;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out128, &id, 128);
+    return LUZRT_OK;
+}
+
+int luzrt_comm_init(luzrt_ctx* c, const void* id128) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, id128, "id128 is null");
+    if (c->world == 1) return LUZRT_OK;
+    if (!g_nccl.load()) return fail(c, LUZRT_E_COMM, "libnccl.so.2 could not be loaded: %s", dlerror());
+    DeviceGuard g(c->device);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
+    if (r != ncclSuccess) return fail(c, LUZRT_E_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    return LUZRT_OK;
+}
+
+int luzrt_resize(luzrt_ctx* c, uint32_t width, uint32_t height) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, width > 0 && height > 0 && width <= 65536 && height <= 65536, "bad image size");
+    REQUIRE(c, height % (uint32_t)c->world == 0, "height must be divisible by the number of ranks");
+    DeviceGuard g(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    free_images(c);
+    const size_t px = (size_t)width * height;
+    CU(c, cudaMalloc(&c->albedo, px * 4));
+    CU(c, cudaMalloc(&c->material, px * 4));
+    CU(c, cudaMalloc(&c->emission, px * 4));
+    CU(c, cudaMalloc(&c->compose, px * 4));
+    CU(c, cudaMalloc(&c->normal, px * 16));
+    CU(c, cudaMalloc(&c->lightA, px * 16));
+    CU(c, cudaMalloc(&c->lightB, px * 16));
+    CU(c, cudaMalloc(&c->lightHist, px * 16));
+    CU(c, cudaMalloc(&c->depth, px * 4));
+    // cleared like the attachments: colour 0, depth 1 (VulkanWrapper.cpp:1194-1196, :1212)
+    CU(c, cudaMemsetAsync(c->albedo, 0, px * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->material, 0, px * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->emission, 0, px * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->compose, 0, px * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->normal, 0, px * 16, c->stream));
+    CU(c, cudaMemsetAsync(c->lightA, 0, px * 16, c->stream));
+    CU(c, cudaMemsetAsync(c->lightB, 0, px * 16, c->stream));
+    CU(c, cudaMemsetAsync(c->lightHist, 0, px * 16, c->stream));
+    {
+        std::vector<float> ones(px, 1.0f);
+        CU(c, cudaMemcpyAsync(c->depth, ones.data(), px * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    c->w = width;
+    c->h = height;
+    c->y0 = (uint32_t)c->rank * (height / (uint32_t)c->world);
+    c->y1 = c->y0 + height / (uint32_t)c->world;
+    c->history_valid = false;
+    c->fc.width = width;
+    c->fc.height = height;
+    return LUZRT_OK;
+}
+
+int luzrt_set_blue_noise(luzrt_ctx* c, const uint8_t* rgba8, uint32_t width, uint32_t height) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, rgba8 && width > 0 && height > 0, "bad blue-noise texture");
+    DeviceGuard g(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->blue_noise) cudaFree(c->blue_noise);
+    c->blue_noise = nullptr;
+    CU(c, cudaMalloc(&c->blue_noise, (size_t)width * height * 4));
+    CU(c, cudaMemcpyAsync(c->blue_noise, rgba8, (size_t)width * height * 4, cudaMemcpyHostToDevice, c->stream));
+    c->bn_w = width;
+    c->bn_h = height;
+    return LUZRT_OK;
+}
+
+int luzrt_texture_create(luzrt_ctx* c, const uint8_t* rgba8, uint32_t width, uint32_t height, int32_t* out_rid) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, rgba8 && width > 0 && height > 0 && out_rid, "bad texture");
+    DeviceGuard g(c->device);
+    Texture t;
+    CU(c, cudaMalloc(&t.data, (size_t)width * height * 4));
+    CU(c, cudaMemcpyAsync(t.data, rgba8, (size_t)width * height * 4, cudaMemcpyHostToDevice, c->stream));
+    t.size = make_uint2(width, height);
+    c->textures.push_back(t);
+    c->tex_dirty = true;
+    *out_rid = (int32_t)c->textures.size() - 1;
+    return LUZRT_OK;
+}
+
+int luzrt_blas_create(luzrt_ctx* c, const void* vertices, uint32_t vertex_count, uint32_t vertex_stride,
+                      const uint32_t* indices, uint32_t index_count, luzrt_blas* out) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, out, "out is null");
+    *out = 0;
+    REQUIRE(c, vertex_stride >= 12 && vertex_stride % 4 == 0, "vertex_stride must be a multiple of 4 and >= 12");
+    const uint32_t n_tris = index_count / 3; // primitiveCount = indexCount / 3 (VulkanWrapper.cpp:761)
+    REQUIRE(c, (vertices && indices) || n_tris == 0, "null vertex/index data");
+    for (uint32_t i = 0; i < 3 * n_tris; i++)
+        if (indices[i] >= vertex_count) return fail(c, LUZRT_E_INVALID, "index %u out of range at %u", indices[i], i);
+    DeviceGuard g(c->device);
+    Blas b;
+    b.alive = true;
+    b.stride = vertex_stride;
+    b.n_verts = vertex_count;
+    b.n_tris = n_tris;
+    int rc = LUZRT_OK;
+    auto bail = [&](int code) {
+        free_blas(b);
+        return code;
+    };
+#define CUB_(expr)                                                                                   \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return bail(fail(c, _e == cudaErrorMemoryAllocation ? LUZRT_E_NOMEM : LUZRT_E_CUDA,     \
+                             "%s: %s", #expr, cudaGetErrorString(_e)));                              \
+    } while (0)
+    CUB_(cudaMalloc(&b.verts, std::max<size_t>((size_t)vertex_count * vertex_stride, 16)));
+    CUB_(cudaMalloc(&b.indices, std::max<size_t>((size_t)n_tris * 12, 16)));
+    if (vertex_count)
+        CUB_(cudaMemcpyAsync(b.verts, vertices, (size_t)vertex_count * vertex_stride, cudaMemcpyHostToDevice, c->stream));
+    if (n_tris) CUB_(cudaMemcpyAsync(b.indices, indices, (size_t)n_tris * 12, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = grow(c, c->d_boxes, c->boxes_cap, std::max<size_t>(n_tris, 1))) != LUZRT_OK) return bail(rc);
+    CUB_(launch_triangle_boxes(c->stream, b.verts, b.stride, b.indices, n_tris, c->d_boxes));
+    c->launches += n_tris ? 1 : 0;
+    CUB_(build_wide_bvh(c->stream, c->scratch, c->d_boxes, n_tris, 3, b.bvh, &c->launches));
+    CUB_(cudaMalloc(&b.tris, std::max<size_t>((size_t)n_tris, 1) * sizeof(WideTri)));
+    CUB_(launch_gather_triangles(c->stream, b.verts, b.stride, b.indices, b.bvh.prim_order, n_tris, b.tris));
+    c->launches += n_tris ? 1 : 0;
+    CUB_(cudaMemcpyAsync(&b.bounds, b.bvh.node_bounds, sizeof(BoxF), cudaMemcpyDeviceToHost, c->stream));
+    CUB_(cudaStreamSynchronize(c->stream));
+    // shrink the node array to its final size (the builder allocates for the worst case)
+    if (b.bvh.node_capacity > (size_t)b.bvh.n_nodes + 16) {
+        WideNode* nn = nullptr;
+        BoxF* nb = nullptr;
+        CUB_(cudaMalloc(&nn, (size_t)b.bvh.n_nodes * sizeof(WideNode)));
+        CUB_(cudaMalloc(&nb, (size_t)b.bvh.n_nodes * sizeof(BoxF)));
+        CUB_(cudaMemcpyAsync(nn, b.bvh.nodes, (size_t)b.bvh.n_nodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, c->stream));
+        CUB_(cudaMemcpyAsync(nb, b.bvh.node_bounds, (size_t)b.bvh.n_nodes * sizeof(BoxF), cudaMemcpyDeviceToDevice, c->stream));
+        CUB_(cudaStreamSynchronize(c->stream));
+        cudaFree(b.bvh.nodes);
+        cudaFree(b.bvh.node_bounds);
+        b.bvh.nodes = nn;
+        b.bvh.node_bounds = nb;
+        b.bvh.node_capacity = b.bvh.n_nodes;
+    }
+#undef CUB_
+    b.levels = (uint32_t)b.bvh.levels.size();
+    // reuse a dead slot if there is one
+    uint32_t slot = 0;
+    for (uint32_t i = 1; i < c->blas.size(); i++)
+        if (!c->blas[i].alive) {
+            slot = i;
+            break;
+        }
+    if (!slot) {
+        c->blas.emplace_back();
+        slot = (uint32_t)c->blas.size() - 1;
+    }
+    c->blas[slot] = b;
+    c->blas_attr_dirty = true;
+    *out = slot;
+    return LUZRT_OK;
+}
+
+int luzrt_blas_destroy(luzrt_ctx* c, luzrt_blas h) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, h > 0 && h < c->blas.size() && c->blas[h].alive, "invalid BLAS handle");
+    DeviceGuard g(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    free_blas(c->blas[h]);
+    c->blas_attr_dirty = true;
+    return LUZRT_OK;
+}
+
+static int dump_bvh(luzrt_ctx* c, const WideBvh& bvh, const void* prims, size_t prim_bytes, void* dst, size_t* bytes) {
+    REQUIRE(c, bytes, "bytes is null");
+    const size_t need = (size_t)bvh.n_nodes * sizeof(WideNode) + prim_bytes;
+    if (!dst || *bytes < need) {
+        *bytes = need;
+        return dst ? fail(c, LUZRT_E_INVALID, "buffer too small") : LUZRT_OK;
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaMemcpy(dst, bvh.nodes, (size_t)bvh.n_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    if (prim_bytes)
+        CU(c, cudaMemcpy((char*)dst + (size_t)bvh.n_nodes * sizeof(WideNode), prims, prim_bytes, cudaMemcpyDeviceToHost));
+    *bytes = need;
+    return LUZRT_OK;
+}
+
+int luzrt_blas_dump(luzrt_ctx* c, luzrt_blas h, void* dst, size_t* bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, h > 0 && h < c->blas.size() && c->blas[h].alive, "invalid BLAS handle");
+    DeviceGuard g(c->device);
+    const Blas& b = c->blas[h];
+    return dump_bvh(c, b.bvh, b.tris, (size_t)b.n_tris * sizeof(WideTri), dst, bytes);
+}
+
+int luzrt_tlas_dump(luzrt_ctx* c, void* dst, size_t* bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, c->have_tlas, "no TLAS built");
+    DeviceGuard g(c->device);
+    // instance records hold device pointers (not reproducible across runs): dump nodes + leaf order
+    return dump_bvh(c, c->tlas, c->tlas.prim_order, (size_t)c->n_inst * sizeof(uint32_t), dst, bytes);
+}
+
+int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t count, int mode) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, instances || count == 0, "instances is null");
+    REQUIRE(c, mode == 0 || mode == 1, "mode must be 0 (rebuild) or 1 (refit)");
+    DeviceGuard g(c->device);
+    uint32_t max_blas_levels = 1;
+    c->host_inst.resize(count);
+    bool same_set = c->have_tlas && c->last_blas.size() == count;
+    for (uint32_t i = 0; i < count; i++) {
+        const luzrt_blas h = instances[i].blas;
+        if (!(h > 0 && h < c->blas.size() && c->blas[h].alive))
+            return fail(c, LUZRT_E_INVALID, "instance %u has an invalid BLAS handle", i);
+        const Blas& b = c->blas[h];
+        InstanceIn& in = c->host_inst[i];
+        memcpy(in.m, instances[i].model_mat, sizeof(in.m));
+        in.nodes = b.bvh.nodes;
+        in.tris = b.tris;
+        in.blas_bounds = b.bounds;
+        in.custom_index = instances[i].custom_index;
+        in.blas_slot = h;
+        max_blas_levels = std::max(max_blas_levels, b.levels);
+        if (same_set && c->last_blas[i] != h) same_set = false;
+    }
+    const bool refit = mode == 1 && same_set && count > 0;
+    const size_t cap_need = std::max<uint32_t>(count, 1);
+    if (c->inst_cap < cap_need) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        void* olds[] = {c->d_inst_in, c->d_recs_in, c->d_recs, c->d_meta_in, c->d_meta};
+        for (void* p : olds)
+            if (p) cudaFree(p);
+        c->d_inst_in = nullptr;
+        c->d_recs_in = c->d_recs = nullptr;
+        c->d_meta_in = c->d_meta = nullptr;
+        c->inst_cap = 0;
+        const size_t n = cap_need + cap_need / 2;
+        CU(c, cudaMalloc(&c->d_inst_in, n * sizeof(InstanceIn)));
+        CU(c, cudaMalloc(&c->d_recs_in, n * sizeof(InstanceRec)));
+        CU(c, cudaMalloc(&c->d_recs, n * sizeof(InstanceRec)));
+        CU(c, cudaMalloc(&c->d_meta_in, n * sizeof(InstanceMeta)));
+        CU(c, cudaMalloc(&c->d_meta, n * sizeof(InstanceMeta)));
+        c->inst_cap = n;
+    }
+    int rc;
+    if ((rc = grow(c, c->d_boxes, c->boxes_cap, cap_need)) != LUZRT_OK) return rc;
+    ev_begin(c, EV_TLAS);
+    if (count)
+        CU(c, cudaMemcpyAsync(c->d_inst_in, c->host_inst.data(), (size_t)count * sizeof(InstanceIn),
+                              cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_instance_prepare(c->stream, c->d_inst_in, count, c->d_boxes, c->d_recs_in, c->d_meta_in));
+    c->launches += count ? 1 : 0;
+    if (refit) {
+        CU(c, refit_wide_bvh(c->stream, c->d_boxes, c->tlas, &c->launches));
+    } else {
+        CU(c, build_wide_bvh(c->stream, c->scratch, c->d_boxes, count, 1, c->tlas, &c->launches));
+    }
+    CU(c, launch_instance_gather(c->stream, c->d_recs_in, c->d_meta_in, c->tlas.prim_order, count, c->d_recs, c->d_meta));
+    c->launches += count ? 1 : 0;
+    ev_end(c, EV_TLAS);
+    c->n_inst = count;
+    c->have_tlas = true;
+    c->last_blas.resize(count);
+    for (uint32_t i = 0; i < count; i++) c->last_blas[i] = instances[i].blas;
+    if (c->tlas.levels.size() + max_blas_levels + 3 > LUZ_STACK_SIZE)
+        return fail(c, LUZRT_E_INVALID, "BVH too deep for the traversal stack (%zu + %u levels)", c->tlas.levels.size(),
+                    max_blas_levels);
+    return LUZRT_OK;
+}
+
+int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_block* extra, uint32_t n_extra) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, s, "scene_block is null");
+    REQUIRE(c, s->num_lights >= 0 && s->num_lights <= LUZW_MAX_LIGHTS, "numLights out of range");
+    REQUIRE(c, extra || n_extra == 0, "extra_lights is null");
+    REQUIRE(c, n_extra == 0 || s->num_lights == LUZW_MAX_LIGHTS, "extra lights require numLights == LUZ_MAX_LIGHTS");
+    REQUIRE(c, s->ao_num_samples >= 0, "aoNumSamples must be >= 0");
+    DeviceGuard g(c->device);
+    const int n = s->num_lights + (int)n_extra;
+    std::vector<LightRec> recs((size_t)std::max(n, 1));
+    uint32_t shadow_bits = 0;
+    for (int i = 0; i < n; i++) {
+        const luzw_light_block& l = i < LUZW_MAX_LIGHTS ? s->lights[i] : extra[i - LUZW_MAX_LIGHTS];
+        if (s->shadow_type == LUZW_SHADOW_MAP && l.shadow_map != -1)
+            return fail(c, LUZRT_E_INVALID, "shadow-map shadows (shadowType 2) are outside this path");
+        LightRec& r = recs[i];
+        r.color_intensity = make_float4(l.color[0], l.color[1], l.color[2], l.intensity);
+        r.position_inner = make_float4(l.position[0], l.position[1], l.position[2], l.inner_angle);
+        r.direction_outer = make_float4(l.direction[0], l.direction[1], l.direction[2], l.outer_angle);
+        r.type = l.type;
+        r.num_shadow_samples = l.num_shadow_samples;
+        r.radius = l.radius;
+        r.shadow_map = l.shadow_map;
+        if (s->shadow_type == LUZW_SHADOW_RAYTRACING && l.num_shadow_samples > 0) shadow_bits += (uint32_t)l.num_shadow_samples;
+    }
+    int rc;
+    if ((rc = grow(c, c->d_lights, c->lights_cap, recs.size())) != LUZRT_OK) return rc;
+    CU(c, cudaMemcpyAsync(c->d_lights, recs.data(), recs.size() * sizeof(LightRec), cudaMemcpyHostToDevice, c->stream));
+    FrameConst& fc = c->fc;
+    memcpy(fc.inverse_proj, s->inverse_proj, 64);
+    memcpy(fc.inverse_view, s->inverse_view, 64);
+    memcpy(fc.view_proj, s->view_proj, 64);
+    memcpy(fc.prev_view_proj, s->prev_view_proj, 64);
+    memcpy(fc.jitter, s->jitter, 8);
+    memcpy(fc.prev_jitter, s->prev_jitter, 8);
+    memcpy(fc.cam_pos, s->cam_pos, 12);
+    for (int k = 0; k < 3; k++) fc.ambient[k] = s->ambient_light_color[k] * s->ambient_light_intensity;
+    fc.ao_min = s->ao_min;
+    fc.ao_max = s->ao_max;
+    fc.ao_num_samples = s->ao_num_samples;
+    fc.num_lights = n;
+    fc.shadow_type = s->shadow_type;
+    c->shadow_bits = shadow_bits;
+    c->rays_per_lit_pixel = shadow_bits + (uint32_t)s->ao_num_samples;
+    c->have_scene = true;
+    return LUZRT_OK;
+}
+
+int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, const void* material,
+                      const void* emission, const void* depth, int src_is_device) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    const size_t px = (size_t)c->w * c->h;
+    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (albedo) CU(c, cudaMemcpyAsync(c->albedo, albedo, px * 4, kind, c->stream));
+    if (normal) CU(c, cudaMemcpyAsync(c->normal, normal, px * 16, kind, c->stream));
+    if (material) CU(c, cudaMemcpyAsync(c->material, material, px * 4, kind, c->stream));
+    if (emission) CU(c, cudaMemcpyAsync(c->emission, emission, px * 4, kind, c->stream));
+    if (depth) CU(c, cudaMemcpyAsync(c->depth, depth, px * 4, kind, c->stream));
+    return LUZRT_OK;
+}
+
+int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_models) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
+    if (!c->have_tlas) return fail(c, LUZRT_E_STATE, "luzrt_tlas_build has not been called");
+    REQUIRE(c, models || n_models == 0, "models is null");
+    DeviceGuard g(c->device);
+    int rc;
+    if ((rc = grow(c, c->d_models, c->models_cap, std::max<size_t>(n_models, 1))) != LUZRT_OK) return rc;
+    if (n_models)
+        CU(c, cudaMemcpyAsync(c->d_models, models, (size_t)n_models * sizeof(luzw_model_block), cudaMemcpyHostToDevice,
+                              c->stream));
+    if (c->blas_attr_dirty) {
+        std::vector<BlasAttr> attr(c->blas.size());
+        for (size_t i = 0; i < c->blas.size(); i++) {
+            const Blas& b = c->blas[i];
+            attr[i] = BlasAttr{b.verts, b.indices, b.stride, (b.alive && b.stride == 48) ? 1u : 0u};
+        }
+        if ((rc = grow(c, c->d_blas_attr, c->blas_attr_cap, attr.size())) != LUZRT_OK) return rc;
+        CU(c, cudaMemcpyAsync(c->d_blas_attr, attr.data(), attr.size() * sizeof(BlasAttr), cudaMemcpyHostToDevice, c->stream));
+        c->blas_attr_dirty = false;
+    }
+    if (c->tex_dirty) {
+        const size_t n = std::max<size_t>(c->textures.size(), 1);
+        std::vector<const uchar4*> ptrs(n, nullptr);
+        std::vector<uint2> sizes(n, make_uint2(0, 0));
+        for (size_t i = 0; i < c->textures.size(); i++) {
+            ptrs[i] = c->textures[i].data;
+            sizes[i] = c->textures[i].size;
+        }
+        if (c->tex_cap < n) {
+            CU(c, cudaStreamSynchronize(c->stream));
+            if (c->d_tex_data) cudaFree(c->d_tex_data);
+            if (c->d_tex_size) cudaFree(c->d_tex_size);
+            c->d_tex_data = nullptr;
+            c->d_tex_size = nullptr;
+            CU(c, cudaMalloc(&c->d_tex_data, n * 2 * sizeof(void*)));
+            CU(c, cudaMalloc(&c->d_tex_size, n * 2 * sizeof(uint2)));
+            c->tex_cap = n * 2;
+        }
+        CU(c, cudaMemcpyAsync(c->d_tex_data, ptrs.data(), n * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_tex_size, sizes.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+        c->tex_dirty = false;
+    }
+    GbufferArgs a{};
+    a.fc = c->fc;
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs};
+    a.inst_meta = c->d_meta;
+    a.blas_attr = c->d_blas_attr;
+    a.models = c->d_models;
+    a.n_models = n_models;
+    a.tex_data = c->d_tex_data;
+    a.tex_size = c->d_tex_size;
+    a.n_textures = (uint32_t)c->textures.size();
+    a.albedo = c->albedo;
+    a.normal = c->normal;
+    a.material = c->material;
+    a.emission = c->emission;
+    a.depth = c->depth;
+    if (c->world == 1) {
+        a.row_start = 0;
+        a.row_count = c->h;
+    } else {
+        a.row_start = (int)c->y0 - 1;
+        a.row_count = (c->y1 - c->y0) + 2;
+    }
+    ev_begin(c, EV_GBUF);
+    CU(c, launch_gbuffer_pass(c->stream, a));
+    c->launches++;
+    ev_end(c, EV_GBUF);
+    return LUZRT_OK;
+}
+
+int luzrt_set_debug(luzrt_ctx* c, uint32_t flags) {
+    if (!c) return LUZRT_E_INVALID;
+    c->debug = flags;
+    return LUZRT_OK;
+}
+
+int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
+    if (!c->have_tlas) return fail(c, LUZRT_E_STATE, "luzrt_tlas_build has not been called");
+    if (!c->blue_noise) return fail(c, LUZRT_E_STATE, "luzrt_set_blue_noise has not been called");
+    DeviceGuard g(c->device);
+    const bool masks = (c->debug & LUZRT_DEBUG_MASKS) != 0, stats = (c->debug & LUZRT_DEBUG_STATS) != 0;
+    const size_t px = (size_t)c->w * c->h;
+    if (masks) {
+        const size_t sw = std::max<size_t>((c->shadow_bits + 31) / 32, 1);
+        const size_t aw = std::max<size_t>(((size_t)c->fc.ao_num_samples + 31) / 32, 1);
+        int rc;
+        if ((rc = grow(c, c->d_shadow_mask, c->shadow_mask_cap, px * sw)) != LUZRT_OK) return rc;
+        if ((rc = grow(c, c->d_ao_mask, c->ao_mask_cap, px * aw)) != LUZRT_OK) return rc;
+        c->shadow_mask_words = sw;
+        c->ao_mask_words = aw;
+    }
+    LightArgs a{};
+    a.fc = c->fc;
+    a.fc.frame_mod = (int)((int32_t)frame % 128); // ctx.frame % 128 on a GLSL int (frameCount < 32768, main.cpp:321)
+    a.fc.bn_w = c->bn_w;
+    a.fc.bn_h = c->bn_h;
+    a.albedo = c->albedo;
+    a.normal = c->normal;
+    a.material = c->material;
+    a.emission = c->emission;
+    a.depth = c->depth;
+    a.blue_noise = c->blue_noise;
+    a.lights = c->d_lights;
+    a.out = c->lightA;
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs};
+    if (c->world == 1) {
+        a.row_start = 0;
+        a.row_count = c->h;
+    } else { // own rows plus the row above and below (wrapping) that TAA's 3x3 taps read
+        a.row_start = (int)c->y0 - 1;
+        a.row_count = (c->y1 - c->y0) + 2;
+    }
+    a.shadow_mask = c->d_shadow_mask;
+    a.shadow_words = (uint32_t)c->shadow_mask_words;
+    a.ao_mask = c->d_ao_mask;
+    a.ao_words = (uint32_t)c->ao_mask_words;
+    a.stats = c->d_stats;
+    a.lit_counters = c->d_lit;
+    ev_begin(c, EV_LIGHT);
+    CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
+    if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
+    CU(c, launch_light_pass(c->stream, a, masks, stats));
+    c->launches++;
+    ev_end(c, EV_LIGHT);
+    return LUZRT_OK;
+}
+
+int luzrt_taa_pass(luzrt_ctx* c, int reconstruct) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
+    DeviceGuard g(c->device);
+    TaaArgs a{};
+    a.fc = c->fc;
+    a.light_in = c->lightA;
+    // the reference never initialises lightHistory (DeferredRenderer.cpp:225-231); this path defines
+    // the first frame after a resize as history == current light buffer
+    a.history = c->history_valid ? c->lightHist : c->lightA;
+    a.depth = c->depth;
+    a.out = c->lightB;
+    a.row_start = c->y0;
+    a.row_count = c->y1 - c->y0;
+    a.reconstruct = reconstruct ? 1 : 0;
+    ev_begin(c, EV_TAA);
+    CU(c, launch_taa_pass(c->stream, a));
+    c->launches++;
+    ev_end(c, EV_TAA);
+    std::swap(c->lightA, c->lightB); // DeferredRenderer.cpp:443
+    return LUZRT_OK;
+}
+
+int luzrt_gather(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    if (c->world == 1) return LUZRT_OK;
+    if (!c->comm) return fail(c, LUZRT_E_STATE, "luzrt_comm_init has not been called");
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    const size_t strip_floats = (size_t)(c->y1 - c->y0) * c->w * 4;
+    ev_begin(c, EV_GATHER);
+    // in place: this rank's strip already sits at its offset inside the full-frame buffer
+    ncclResult_t r = g_nccl.AllGather((const float*)c->lightA + (size_t)c->rank * strip_floats, c->lightA, strip_floats,
+                                      ncclFloat, c->comm, c->stream);
+    ev_end(c, EV_GATHER);
+    if (r != ncclSuccess) return fail(c, LUZRT_E_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    return LUZRT_OK;
+}
+
+int luzrt_compose_pass(luzrt_ctx* c, float exposure) {
+    if (!c) return LUZRT_E_INVALID;
+    (void)exposure; // present.frag's active path (TonemapACES, :87) ignores ctx.exposure
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    ev_begin(c, EV_COMPOSE);
+    CU(c, launch_compose_pass(c->stream, c->lightA, c->compose, c->w, c->y0, c->y1 - c->y0));
+    c->launches++;
+    ev_end(c, EV_COMPOSE);
+    return LUZRT_OK;
+}
+
+int luzrt_swap_light_history(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    std::swap(c->lightA, c->lightHist); // DeferredRenderer.cpp:469-471
+    c->history_valid = true;
+    return LUZRT_OK;
+}
+
+int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, dst, "dst is null");
+    DeviceGuard g(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (which == LUZRT_STATS) {
+        REQUIRE(c, bytes >= sizeof(luzrt_stats), "buffer too small for luzrt_stats");
+        DeviceStats ds{};
+        unsigned long long lit[64 * 16];
+        CU(c, cudaMemcpy(&ds, c->d_stats, sizeof(ds), cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(lit, c->d_lit, sizeof(lit), cudaMemcpyDeviceToHost));
+        luzrt_stats s{};
+        for (int i = 0; i < 64; i++) s.lit_pixels += lit[16 * i];
+        if (c->debug & LUZRT_DEBUG_STATS) {
+            s.rays = ds.rays;
+            s.nodes_visited = ds.nodes;
+            s.triangles_tested = ds.tris;
+            s.instances_entered = ds.insts;
+            s.rays_occluded = ds.occluded;
+        } else { // every lit pixel traces the same number of rays
+            s.rays = s.lit_pixels * c->rays_per_lit_pixel;
+        }
+        memcpy(dst, &s, sizeof(s));
+        return LUZRT_OK;
+    }
+    if (which == LUZRT_TIMINGS) {
+        REQUIRE(c, bytes >= sizeof(luzrt_timings), "buffer too small for luzrt_timings");
+        float ms[EV_COUNT] = {0};
+        for (int i = 0; i < EV_COUNT; i++)
+            if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], c->ev[i][0], c->ev[i][1]);
+        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE]};
+        memcpy(dst, &t, sizeof(t));
+        return LUZRT_OK;
+    }
+    size_t have = 0;
+    void* src = image_ptr(c, which, &have);
+    if (!src) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
+    REQUIRE(c, bytes >= have, "destination buffer too small");
+    CU(c, cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
+    return LUZRT_OK;
+}
+
+int luzrt_device_ptr(luzrt_ctx* c, int which, void** out_ptr, size_t* out_bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, out_ptr && out_bytes, "null output");
+    *out_ptr = image_ptr(c, which, out_bytes);
+    return *out_ptr ? LUZRT_OK : fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
+}
+
+int luzrt_sync(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    DeviceGuard g(c->device);
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LUZRT_OK;
+}
+
+int luzrt_stream(luzrt_ctx* c, uint64_t* out_stream) {
+    if (!c || !out_stream) return LUZRT_E_INVALID;
+    *out_stream = (uint64_t)(uintptr_t)c->stream;
+    return LUZRT_OK;
+}
+
+uint64_t luzrt_launch_count(luzrt_ctx* c) { return c ? c->launches : 0; }
+
+} // extern "C"

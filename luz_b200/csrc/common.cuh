@@ -1,0 +1,139 @@
+// common.cuh -- shared types for libluzrt (sm_100a).  See DESIGN.md for the memory layout.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/luzrt.h"
+
+namespace luz {
+
+// ---- 8-wide compressed BVH node, 80 bytes, read as five 16-byte loads -------------------------
+// Layout after Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through
+// Compressed Wide BVHs" (HPG 2017): child boxes are 8-bit offsets from the node origin p on a
+// per-axis power-of-two grid 2^(e-127).
+//   meta[i] == 0                      : empty slot
+//   meta[i] == (1<<5) | (24 + i)      : internal child; its index is child_base + popc(imask & ((1<<i)-1))
+//   meta[i] == (unary(count)<<5) | off: leaf of `count` (1..3) primitives prim_base + off .. +count-1
+struct __align__(16) WideNode {
+    float px, py, pz;
+    uint8_t ex, ey, ez, imask;
+    uint32_t child_base;
+    uint32_t prim_base;
+    uint8_t meta[8];
+    uint8_t qlox[8], qloy[8], qloz[8];
+    uint8_t qhix[8], qhiy[8], qhiz[8];
+};
+static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+
+// One triangle, 48 bytes: three float4 (xyz = vertex, v0.w = original triangle index bits).
+struct __align__(16) WideTri {
+    float4 v0, v1, v2;
+};
+static_assert(sizeof(WideTri) == 48, "WideTri must be 48 bytes");
+
+// One TLAS leaf record, 64 bytes: world->object 3x4 (rows) + the BLAS it points to.
+struct __align__(16) InstanceRec {
+    float4 r0, r1, r2; // rows of the inverse affine transform
+    const WideNode* nodes;
+    const WideTri* tris;
+};
+static_assert(sizeof(InstanceRec) == 64, "InstanceRec must be 64 bytes");
+
+struct InstanceMeta { // parallel to InstanceRec (G-buffer pass only)
+    uint32_t custom_index;
+    uint32_t blas_slot;
+};
+
+struct BlasAttr { // per-BLAS vertex attributes kept for the G-buffer pass
+    const uint8_t* vertices;
+    const uint32_t* indices;
+    uint32_t stride;
+    uint32_t has_attr;
+};
+
+struct TraceScene {
+    const WideNode* tlas_nodes;
+    const InstanceRec* instances;
+};
+
+// compact light record staged in shared memory (first 64 bytes of a LightBlock)
+struct __align__(16) LightRec {
+    float4 color_intensity;
+    float4 position_inner;
+    float4 direction_outer;
+    int type;
+    int num_shadow_samples;
+    float radius;
+    int shadow_map;
+};
+static_assert(sizeof(LightRec) == 64, "LightRec");
+
+struct FrameConst { // what the kernels need from SceneBlock, passed by value (kernel param space)
+    float inverse_proj[16];
+    float inverse_view[16];
+    float view_proj[16];
+    float prev_view_proj[16];
+    float jitter[2], prev_jitter[2];
+    float cam_pos[3];
+    float ambient[3]; // ambientLightColor * ambientLightIntensity
+    float ao_min, ao_max;
+    int ao_num_samples;
+    int num_lights;
+    int shadow_type;
+    int frame_mod; // frame % 128
+    uint32_t width, height;
+    uint32_t bn_w, bn_h;
+};
+
+struct DeviceStats {
+    unsigned long long lit_pixels, rays, nodes, tris, insts, occluded;
+};
+
+// ---- small vector helpers ------------------------------------------------------------------
+__host__ __device__ inline float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__host__ __device__ inline float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__host__ __device__ inline float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__host__ __device__ inline float3 operator-(float3 a) { return f3(-a.x, -a.y, -a.z); }
+__host__ __device__ inline float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__host__ __device__ inline float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ inline float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__host__ __device__ inline float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__host__ __device__ inline float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
+__host__ __device__ inline float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ inline float3 cross3(float3 a, float3 b) {
+    return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
+}
+__device__ inline float length3(float3 a) { return sqrtf(dot3(a, a)); }
+__device__ inline float3 normalize3(float3 a) { return a / sqrtf(dot3(a, a)); }
+__device__ inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+__host__ __device__ inline float4 f4(float x, float y, float z, float w) { return make_float4(x, y, z, w); }
+__host__ __device__ inline float4 operator+(float4 a, float4 b) { return f4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__host__ __device__ inline float4 operator-(float4 a, float4 b) { return f4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+__host__ __device__ inline float4 operator*(float4 a, float s) { return f4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__host__ __device__ inline float4 operator/(float4 a, float s) { return f4(a.x / s, a.y / s, a.z / s, a.w / s); }
+__device__ inline float4 min4(float4 a, float4 b) { return f4(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z), fminf(a.w, b.w)); }
+__device__ inline float4 max4(float4 a, float4 b) { return f4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w)); }
+__device__ inline bool any_nan4(float4 a) { return isnan(a.x) || isnan(a.y) || isnan(a.z) || isnan(a.w); }
+
+// column-major mat4 * vec4, summed left to right over columns
+__device__ inline float4 mat_mul(const float* m, float4 v) {
+    float4 r;
+    r.x = m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * v.w;
+    r.y = m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * v.w;
+    r.z = m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w;
+    r.w = m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w;
+    return r;
+}
+
+// utils.glsl:1-7
+__device__ inline float3 depth_to_world(const FrameConst& fc, float u, float v, float depth) {
+    float4 clip = f4(u * 2.0f - 1.0f, v * 2.0f - 1.0f, depth, 1.0f);
+    float4 view = mat_mul(fc.inverse_proj, clip);
+    view = view / view.w;
+    float4 world = mat_mul(fc.inverse_view, view);
+    return f3(world.x, world.y, world.z);
+}
+
+} // namespace luz

@@ -1,0 +1,264 @@
+// light_pass.cu -- the fused deferred lighting kernel: G-buffer decode, Cook-Torrance shading,
+// shadow-ray and AO-ray generation, any-hit traversal and accumulation in one launch, with all
+// per-ray state in registers (no ray buffers ever touch HBM).
+//
+// Restates source/Shaders/light.frag:171-235 (main), :86-109 (TraceShadowRay), :111-135
+// (TraceAORays), :137-169 (EvaluateShadow), :57-75 (samplers) and :17-49 (BRDF) of the reference;
+// launched where DeferredRenderer::LightPass (DeferredRenderer.cpp:324-345) draws its quad.
+// One warp shades an 8x4 pixel tile; the light list is staged in shared memory.
+#include "passes.h"
+#include "traverse.cuh"
+
+namespace luz {
+
+namespace {
+
+constexpr float kPI = 3.14159265359f;              // LuzCommon.h:11
+constexpr float kGoldenRatio = 2.118033988749895f; // LuzCommon.h:12 (sic)
+constexpr int kLightChunk = 256;
+
+__device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
+
+// light.frag:71-75.  The multiply and the add are rounded separately (no FMA) so that the sample
+// sequence is bit-identical to the oracle's plain fp32 evaluation.
+__device__ __forceinline__ float2 blue_noise_sample(float bn_r, float bn_g, int i, int frame_mod) {
+    const float k = (float)(128 * i + frame_mod);
+    const float off = __fmul_rn(kGoldenRatio, k);
+    return make_float2(fractf(__fadd_rn(bn_r, off)), fractf(__fadd_rn(bn_g, off)));
+}
+
+// light.frag:17-26
+__device__ __forceinline__ float distribution_ggx(float3 N, float3 H, float roughness) {
+    const float a = roughness * roughness;
+    const float a2 = a * a;
+    const float NdotH = fmaxf(dot3(N, H), 0.0f);
+    const float NdotH2 = NdotH * NdotH;
+    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
+    denom = kPI * denom * denom;
+    return a2 / denom;
+}
+// light.frag:28-36
+__device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughness) {
+    const float r = roughness + 1.0f;
+    const float k = (r * r) / 8.0f;
+    return NdotV / (NdotV * (1.0f - k) + k);
+}
+
+template <bool MASKS, bool STATS>
+__global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
+    __shared__ unsigned int s_lit;
+
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t r = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool in_image = x < fc.width && r < a.row_count;
+    uint32_t y = 0;
+    if (in_image) {
+        int yy = (a.row_start + (int)r) % (int)fc.height;
+        if (yy < 0) yy += (int)fc.height;
+        y = (uint32_t)yy;
+    }
+    const size_t pix = (size_t)y * fc.width + x;
+    if (threadIdx.x == 0) s_lit = 0;
+
+    // ---- G-buffer fetch (light.frag:172-176; texel loads) ----
+    float3 N = f3(0.0f, 0.0f, 0.0f);
+    uchar4 a8 = make_uchar4(0, 0, 0, 0), m8 = a8, e8 = a8;
+    float depth = 1.0f;
+    uchar4 bn8 = a8;
+    if (in_image) {
+        const float4 n4 = __ldg(a.normal + pix);
+        N = f3(n4.x, n4.y, n4.z);
+        a8 = __ldg(a.albedo + pix);
+        m8 = __ldg(a.material + pix);
+        e8 = __ldg(a.emission + pix);
+        depth = __ldg(a.depth + pix);
+        // gl_FragCoord = (x+.5, y+.5); ivec2(mod(fragCoord, size)) == (x % w, y % h)
+        bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+    }
+    const float3 ambientLight = f3(fc.ambient[0], fc.ambient[1], fc.ambient[2]);
+    const bool lit = in_image && (length3(N) != 0.0f); // :178
+    if (in_image && !lit) a.out[pix] = make_float4(ambientLight.x, ambientLight.y, ambientLight.z, 1.0f);
+
+    const float3 albedo = f3(powf((float)a8.x / 255.0f, 2.2f), powf((float)a8.y / 255.0f, 2.2f),
+                             powf((float)a8.z / 255.0f, 2.2f));
+    const float roughness = (float)m8.x / 255.0f, metallic = (float)m8.y / 255.0f, occlusion = (float)m8.z / 255.0f;
+    const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+    const float3 fragPos = depth_to_world(fc, u, v, depth);
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const float3 V = normalize3(camPos - fragPos);
+    const float3 F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - metallic) + albedo * metallic;
+    const float camDist = length3(fragPos - camPos);
+    const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+    const float NdotV = fmaxf(dot3(N, V), 0.0f);
+    const float ggxV = geometry_schlick_ggx(NdotV, roughness);
+
+    float3 Lo = f3(0.0f, 0.0f, 0.0f);
+    LocalStats st = {0, 0, 0};
+    uint32_t n_rays = 0, n_occl = 0;
+    uint32_t* smask = nullptr;
+    uint32_t* amask = nullptr;
+    if (MASKS && in_image) {
+        smask = a.shadow_mask + pix * a.shadow_words;
+        amask = a.ao_mask + pix * a.ao_words;
+        for (uint32_t k = 0; k < a.shadow_words; k++) smask[k] = 0;
+        for (uint32_t k = 0; k < a.ao_words; k++) amask[k] = 0;
+    }
+    uint32_t shadow_bit = 0;
+
+    for (int base = 0; base < fc.num_lights; base += kLightChunk) {
+        const int chunk = min(kLightChunk, fc.num_lights - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < chunk * 4; k += blockDim.x)
+            reinterpret_cast<float4*>(s_lights)[k] = __ldg(reinterpret_cast<const float4*>(a.lights + base) + k);
+        __syncthreads();
+        if (!lit) continue;
+        for (int li = 0; li < chunk; li++) {
+            const LightRec L4 = s_lights[li];
+            const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
+            const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
+            const float3 Lvec = lpos - fragPos;
+            const float dist = length3(Lvec);
+            float3 L = Lvec / dist; // normalize(L_)
+            float attenuation = 1.0f;
+            if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
+                L = normalize3(-ldir);
+            } else if (L4.type == LUZW_LIGHT_SPOT) {
+                attenuation = 1.0f / (dist * dist);
+                const float theta = dot3(L, normalize3(-ldir));
+                const float epsilon = L4.position_inner.w - L4.direction_outer.w;
+                attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
+            } else if (L4.type == LUZW_LIGHT_POINT) {
+                attenuation = 1.0f / (dist * dist);
+            }
+            // ---- EvaluateShadow (light.frag:137-169) ----
+            float shadowFactor = 1.0f;
+            if (fc.shadow_type == LUZW_SHADOW_RAYTRACING) {
+                const float numSamples = (float)L4.num_shadow_samples;
+                shadowFactor = 0.0f;
+                if (numSamples != 0.0f) { // TraceShadowRay :86-109
+                    const float shadowBias = fmaxf(camDist * 0.01f, 0.05f);
+                    const float3 O = fragPos + N * shadowBias;
+                    const float3 Lr = (L4.type == LUZW_LIGHT_DIRECTIONAL) ? ldir * dot3(ldir, L) * dist : L * dist;
+                    const float3 T = normalize3(cross3(Lr, f3(0.0f, 1.0f, 0.0f)));
+                    const float3 B = normalize3(cross3(T, Lr));
+                    const float tMax = length3(Lr);
+                    float numShadows = 0.0f;
+                    for (int i = 0; (float)i < numSamples; i++) {
+                        const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
+                        const float pointRadius = L4.radius * sqrtf(rng.x);
+                        const float pointAngle = rng.y * 2.0f * kPI;
+                        float sn, cs;
+                        sincosf(pointAngle, &sn, &cs);
+                        const float dx = pointRadius * cs, dy = pointRadius * sn;
+                        const float3 dir = normalize3(Lr + dx * T + dy * B);
+                        n_rays++;
+                        if (trace_ray<false, STATS>(a.scene, O, dir, 0.001f, tMax, nullptr, &st)) {
+                            numShadows += 1.0f;
+                            n_occl++;
+                            if (MASKS) {
+                                const uint32_t b = shadow_bit + (uint32_t)i;
+                                smask[b >> 5] |= 1u << (b & 31u);
+                            }
+                        }
+                    }
+                    shadowFactor = numShadows / numSamples;
+                }
+                shadow_bit += (uint32_t)max(L4.num_shadow_samples, 0);
+            }
+            const float3 lcol = f3(L4.color_intensity.x, L4.color_intensity.y, L4.color_intensity.z);
+            const float3 radiance = lcol * L4.color_intensity.w * attenuation * (1.0f - shadowFactor);
+
+            const float3 H = normalize3(V + L);
+            const float NDF = distribution_ggx(N, H, roughness);
+            const float NdotL = fmaxf(dot3(N, L), 0.0f);
+            const float G = geometry_schlick_ggx(NdotL, roughness) * ggxV; // GeometrySmith :38-45
+            const float fp = powf(clampf(1.0f - clampf(dot3(H, V), 0.0f, 1.0f), 0.0f, 1.0f), 5.0f);
+            const float3 F = F0 + (f3(1.0f, 1.0f, 1.0f) - F0) * fp; // FresnelSchlick :47-49
+            const float3 num = NDF * G * F;
+            const float denom = 4.0f * NdotV * NdotL + 0.0001f;
+            const float3 spec = num / denom;
+            float3 kD = f3(1.0f, 1.0f, 1.0f) - F;
+            kD = kD * (1.0f - metallic);
+            Lo = Lo + (kD * albedo / kPI + spec) * radiance * NdotL;
+        }
+    }
+
+    if (lit) {
+        // ---- TraceAORays (light.frag:111-135, :229-231) ----
+        float rayTracedAo = 1.0f;
+        if (fc.ao_num_samples != 0) {
+            const float aoBias = camDist * 0.01f;
+            const float3 P = fragPos + N * aoBias;
+            const float3 tangent = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+            const float3 bitangent = cross3(N, tangent);
+            float ao = 0.0f;
+            for (int i = 0; i < fc.ao_num_samples; i++) {
+                const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
+                const float rr = sqrtf(rng.x);
+                const float theta = 6.283f * rng.y;
+                float sn, cs;
+                sincosf(theta, &sn, &cs);
+                const float hx = rr * cs, hy = rr * sn, hz = sqrtf(fmaxf(0.0f, 1.0f - rng.x));
+                const float3 dir = tangent * hx + bitangent * hy + N * hz;
+                n_rays++;
+                if (!trace_ray<false, STATS>(a.scene, P, dir, fc.ao_min, fc.ao_max, nullptr, &st)) {
+                    ao += 1.0f;
+                } else {
+                    n_occl++;
+                    if (MASKS) amask[i >> 5] |= 1u << (i & 31);
+                }
+            }
+            rayTracedAo = ao / (float)fc.ao_num_samples;
+        }
+        const float3 emission = f3((float)e8.x / 255.0f, (float)e8.y / 255.0f, (float)e8.z / 255.0f);
+        const float3 ambient = ambientLight * albedo * occlusion * rayTracedAo;
+        const float3 color = ambient + Lo + emission;
+        a.out[pix] = make_float4(color.x, color.y, color.z, 1.0f);
+    }
+
+    // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
+    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit));
+    if (lane == 0 && lit_warp) atomicAdd(&s_lit, lit_warp);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_lit)
+        atomicAdd(a.lit_counters + 16 * ((blockIdx.x + blockIdx.y * 7u) & 63u), (unsigned long long)s_lit);
+    if (STATS) {
+        unsigned long long vals[5] = {n_rays, st.nodes, st.tris, st.insts, n_occl};
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            unsigned long long vsum = vals[k];
+            for (int off = 16; off; off >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, off);
+            vals[k] = vsum;
+        }
+        if (lane == 0) {
+            atomicAdd(&a.stats->rays, vals[0]);
+            atomicAdd(&a.stats->nodes, vals[1]);
+            atomicAdd(&a.stats->tris, vals[2]);
+            atomicAdd(&a.stats->insts, vals[3]);
+            atomicAdd(&a.stats->occluded, vals[4]);
+        }
+    }
+}
+
+} // namespace
+
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats) {
+    if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;
+    const dim3 grid((args.fc.width + 15) / 16, (args.row_count + 7) / 8);
+    const size_t smem = sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk));
+    if (masks && stats)
+        k_light_pass<true, true><<<grid, 128, smem, stream>>>(args);
+    else if (masks)
+        k_light_pass<true, false><<<grid, 128, smem, stream>>>(args);
+    else if (stats)
+        k_light_pass<false, true><<<grid, 128, smem, stream>>>(args);
+    else
+        k_light_pass<false, false><<<grid, 128, smem, stream>>>(args);
+    return cudaGetLastError();
+}
+
+} // namespace luz

@@ -1,0 +1,66 @@
+// passes.h -- launch interfaces of the frame kernels (light, TAA, compose, G-buffer).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace luz {
+
+struct LightArgs {
+    FrameConst fc;
+    const uchar4* albedo;
+    const float4* normal;
+    const uchar4* material;
+    const uchar4* emission;
+    const float* depth;
+    const uchar4* blue_noise;
+    const LightRec* lights;
+    float4* out;
+    TraceScene scene;
+    int row_start;      // first image row to shade (may be negative / beyond H: rows wrap like the
+    uint32_t row_count; // REPEAT sampler TAA reads them with)
+    uint32_t* shadow_mask;
+    uint32_t shadow_words;
+    uint32_t* ao_mask;
+    uint32_t ao_words;
+    DeviceStats* stats;
+    unsigned long long* lit_counters; // 64 counters, 128 B apart
+};
+
+struct TaaArgs {
+    FrameConst fc;
+    const float4* light_in;
+    const float4* history;
+    const float* depth;
+    float4* out;
+    uint32_t row_start, row_count;
+    int reconstruct;
+};
+
+struct GbufferArgs {
+    FrameConst fc;
+    TraceScene scene;
+    const InstanceMeta* inst_meta;
+    const BlasAttr* blas_attr;
+    const luzw_model_block* models;
+    uint32_t n_models;
+    const uchar4* const* tex_data; // per RID: device pointer (or null)
+    const uint2* tex_size;
+    uint32_t n_textures;
+    uchar4* albedo;
+    float4* normal;
+    uchar4* material;
+    uchar4* emission;
+    float* depth;
+    int row_start;
+    uint32_t row_count;
+};
+
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats);
+cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
+cudaError_t launch_compose_pass(cudaStream_t stream, const float4* light_in, uchar4* out_bgra, uint32_t width,
+                                uint32_t row_start, uint32_t row_count);
+cudaError_t launch_gbuffer_pass(cudaStream_t stream, const GbufferArgs& args);
+
+} // namespace luz

@@ -1,0 +1,326 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libluzrt.so), against the CPU oracle
+on identical inputs.  Gates (BASELINE.json north_star): shadow/AO visibility masks agree on
+>= 99.9 % of rays; radiance max-abs <= 1e-3 in linear HDR or PSNR >= 50 dB; BVH build bitwise
+deterministic."""
+import numpy as np
+import pytest
+
+import oracle_api as O
+import scene_util as S
+from luz_b200 import rt as R
+
+pytestmark = pytest.mark.gpu
+
+MASK_AGREE = 0.999
+RADIANCE_TOL = 1e-3
+
+
+def popcount(a):
+    return int(np.unpackbits(np.ascontiguousarray(a).view(np.uint8)).sum())
+
+
+def psnr(a, b):
+    mse = float(np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2))
+    peak = float(max(np.abs(b).max(), 1e-12))
+    return 99.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+def check_radiance(got, ref, what):
+    err = float(np.abs(got - ref).max())
+    p = psnr(got, ref)
+    assert err <= RADIANCE_TOL or p >= 50.0, "%s: max-abs %.3g, PSNR %.1f dB" % (what, err, p)
+    return err, p
+
+
+def run_light(rt, sc, gb, frame, bn, extra=None):
+    rt.set_scene(sc["scene"], extra)
+    rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
+    rt.set_debug(R.DEBUG_MASKS | R.DEBUG_STATS)
+    rt.light_pass(frame)
+    out = rt.read(R.IMG_LIGHT)
+    return out, rt.read(R.SHADOW_MASK), rt.read(R.AO_MASK), rt.read(R.STATS)
+
+
+def compare_light(sc, w, h, frame, rt, exhaustive, extra=None):
+    world = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h,
+                        exhaustive=exhaustive)
+    bn = S.blue_noise()
+    n_l = sc["scene"].num_lights + (len(extra) if extra is not None else 0)
+    srays = sum((sc["scene"].lights[i].num_shadow_samples if i < 64 else extra[i - 64].num_shadow_samples)
+                for i in range(n_l)) if sc["scene"].shadow_type == 1 else 0
+    sw = max((srays + 31) // 32, 1)
+    aw = max((sc["scene"].ao_num_samples + 31) // 32, 1)
+    rc, ref, sm, am, st = O.light_pass(sc["scene"], gb, frame, bn, world, extra_lights=extra, exhaustive=exhaustive,
+                                       shadow_words=sw, ao_words=aw)
+    assert rc == 0
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+    S.make_rt_scene(rt, sc)
+    out, gsm, gam, gst = run_light(rt, sc, gb, frame, bn, extra)
+    assert gst.lit_pixels == st.lit_pixels
+    assert gst.rays == st.rays
+    assert gsm.shape == sm.shape and gam.shape == am.shape
+    bad = popcount(gsm ^ sm) + popcount(gam ^ am)
+    agree = 1.0 - bad / max(st.rays, 1)
+    assert agree >= MASK_AGREE, "visibility agreement %.5f (%d of %d rays differ)" % (agree, bad, st.rays)
+    # radiance: pixels whose masks agree must match tightly; the whole image must pass the gate
+    same = np.all(gsm == sm, axis=-1) & np.all(gam == am, axis=-1)
+    if same.any():
+        e = float(np.abs(out[same] - ref[same]).max())
+        assert e <= RADIANCE_TOL, "radiance on mask-identical pixels differs by %.3g" % e
+    err, p = check_radiance(out, ref, "light pass")
+    return dict(agree=agree, err=err, psnr=p, rays=st.rays, gb=gb, ref=ref, out=out, stats=gst)
+
+
+def test_default_scene_c1(rt_factory):
+    """Config C1: assets/default.luz at 1280x720, 1 shadow ray/light + 1 AO ray/px, exhaustive oracle."""
+    rt = rt_factory()
+    sc = S.default_scene(frame=0, light_samples=1, ao_samples=1)
+    r = compare_light(sc, 1280, 720, 0, rt, exhaustive=True)
+    assert r["rays"] > 800000
+    print("C1: agree %.6f max-abs %.3g psnr %.1f rays %d nodes/ray %.2f tris/ray %.2f" % (
+        r["agree"], r["err"], r["psnr"], r["rays"], r["stats"].nodes_visited / r["rays"],
+        r["stats"].triangles_tested / r["rays"]))
+
+
+def test_default_scene_file_settings(rt_factory):
+    """default.luz's own settings (lightSamples 2, aoSamples 4) on a later frame of the jitter cycle."""
+    rt = rt_factory()
+    sc = S.default_scene(frame=5, light_samples=2, ao_samples=4)
+    compare_light(sc, 640, 360, 5 + 128 * 3, rt, exhaustive=True)
+
+
+def test_synthetic_multi_light(rt_factory):
+    """Instanced cubes, point + spot + directional lights, mixed materials (BVH2 oracle)."""
+    rt = rt_factory()
+    sc = S.synthetic_scene(512, 288, grid=5, n_lights=4, light_samples=2, ao_samples=3)
+    r = compare_light(sc, 512, 288, 77, rt, exhaustive=False)
+    assert r["rays"] > 100000
+
+
+def test_shadow_type_disabled_and_no_samples(rt_factory):
+    """shadowType 0 => every light fully shadowed (light.frag:166-168); RT with 0 samples => unshadowed."""
+    rt = rt_factory()
+    for st, ls in ((0, 1), (1, 0)):
+        sc = S.synthetic_scene(256, 144, grid=3, n_lights=3, light_samples=ls, ao_samples=0, shadow_type=st)
+        r = compare_light(sc, 256, 144, 3, rt, exhaustive=False)
+        assert r["stats"].rays == 0
+
+
+def test_extra_lights_beyond_64(rt_factory):
+    """Config C4's mechanism: lights 64.. go through extra_lights."""
+    from luz_b200 import wire
+    rt = rt_factory()
+    sc = S.synthetic_scene(192, 108, grid=3, n_lights=3, light_samples=1, ao_samples=0)
+    sb = sc["scene"]
+    rng = np.random.default_rng(7)
+    extra = (wire.LightBlock * 8)()
+    blocks = [sb.lights[i] for i in range(64)] + [extra[i] for i in range(8)]
+    for i, lb in enumerate(blocks):
+        lb.type = wire.LIGHT_SPOT if i % 4 == 0 else wire.LIGHT_POINT
+        for k in range(3):
+            lb.color[k] = 1.0
+        lb.position[0], lb.position[1], lb.position[2] = (float(rng.uniform(-5, 5)), 6.0, float(rng.uniform(-5, 5)))
+        lb.direction[0], lb.direction[1], lb.direction[2] = 0.1, -1.0, 0.05
+        lb.intensity, lb.radius = 1.0, 0.2
+        lb.inner_angle, lb.outer_angle = float(np.radians(60)), float(np.radians(50))
+        lb.num_shadow_samples, lb.shadow_map = 1, -1
+    sb.num_lights = 64
+    r = compare_light(sc, 192, 108, 9, rt, exhaustive=False, extra=extra)
+    assert r["rays"] == r["stats"].lit_pixels * 72
+
+
+def test_adversarial_gbuffer(rt_factory):
+    """Uniform-random G-buffer (seed 99): roughness 0, non-unit normals, depth-1 pixels with N != 0."""
+    rt = rt_factory()
+    w, h = 256, 128
+    sc = S.synthetic_scene(w, h, grid=3, n_lights=3, light_samples=1, ao_samples=2)
+    world = O.World(sc["meshes"], sc["instances"])
+    rng = np.random.default_rng(99)
+    gb = O.GBuffer(w, h)
+    gb.albedo[:] = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    gb.material[:] = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    gb.material[::3, :, 0] = 0
+    gb.emission[:] = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    gb.normal[..., :3] = rng.normal(0, 1, (h, w, 3)).astype(np.float32) * rng.uniform(0.2, 2.0, (h, w, 1)).astype(np.float32)
+    gb.normal[::7, ::5] = 0
+    gb.depth[:] = rng.uniform(0.9990, 1.0, (h, w)).astype(np.float32)
+    gb.depth[::4, ::4] = 1.0
+    bn = S.blue_noise()
+    rc, ref, sm, am, st = O.light_pass(sc["scene"], gb, 200, bn, world, exhaustive=False, shadow_words=1, ao_words=1)
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+    S.make_rt_scene(rt, sc)
+    out, gsm, gam, gst = run_light(rt, sc, gb, 200, bn)
+    assert gst.rays == st.rays
+    bad = popcount(gsm ^ sm) + popcount(gam ^ am)
+    assert 1.0 - bad / st.rays >= MASK_AGREE
+    same = np.all(gsm == sm, axis=-1) & np.all(gam == am, axis=-1)
+    fin = np.isfinite(ref).all(axis=-1) & same
+    assert np.array_equal(np.isnan(out), np.isnan(ref)) or (np.isnan(out) != np.isnan(ref)).mean() < 1e-3
+    rel = np.abs(out[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1.0)
+    assert float(rel.max()) <= 2e-3, float(rel.max())
+
+
+def test_taa_parity(rt_factory):
+    rt = rt_factory()
+    w, h = 512, 288
+    sc = S.synthetic_scene(w, h, grid=4, n_lights=3, light_samples=1, ao_samples=2)
+    r = compare_light(sc, w, h, 11, rt, exhaustive=False)
+    gb = r["gb"]
+    for reconstruct in (True, False):
+        # frame 0: history := current light
+        rt.resize(w, h)
+        rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
+        rt.set_scene(sc["scene"])
+        rt.set_debug(0)
+        rt.light_pass(11)
+        light0 = rt.read(R.IMG_LIGHT)
+        rt.taa_pass(reconstruct)
+        res0 = rt.read(R.IMG_LIGHT)
+        ref0 = O.taa_pass(sc["scene"], light0, light0, gb.depth, reconstruct)
+        assert float(np.abs(res0 - ref0).max()) <= 1e-4
+        rt.swap_light_history()
+        # frame 1: genuine history, other blue-noise offset
+        rt.light_pass(12)
+        light1 = rt.read(R.IMG_LIGHT)
+        rt.taa_pass(reconstruct)
+        res1 = rt.read(R.IMG_LIGHT)
+        ref1 = O.taa_pass(sc["scene"], light1, res0, gb.depth, reconstruct)
+        assert float(np.abs(res1 - ref1).max()) <= 1e-4
+        rt.swap_light_history()
+        assert np.array_equal(rt.read(R.IMG_HISTORY), res1)
+        # compose
+        rt.swap_light_history()
+        rt.compose_pass(2.0)
+        comp = rt.read(R.IMG_COMPOSE)
+        refc = O.compose_pass(res1)
+        assert int(np.abs(comp.astype(int) - refc.astype(int)).max()) <= 1
+
+
+def test_gbuffer_pass_parity(rt_factory):
+    """CUDA primary-visibility G-buffer against the oracle's generator (input producer, section 8f)."""
+    rt = rt_factory()
+    for sc, (w, h) in ((S.default_scene(frame=2), (640, 360)), (S.synthetic_scene(384, 216, grid=4), (384, 216))):
+        world = O.World(sc["meshes"], sc["instances"])
+        ref = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h,
+                             exhaustive=True)
+        rt.resize(w, h)
+        S.make_rt_scene(rt, sc)
+        rt.set_scene(sc["scene"])
+        rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+        n = rt.read(R.GBUF_NORMAL)
+        d = rt.read(R.GBUF_DEPTH)
+        a = rt.read(R.GBUF_ALBEDO)
+        m = rt.read(R.GBUF_MATERIAL)
+        e = rt.read(R.GBUF_EMISSION)
+        same_cov = (np.linalg.norm(n[..., :3], axis=-1) > 0) == (np.linalg.norm(ref.normal[..., :3], axis=-1) > 0)
+        assert same_cov.mean() > 0.999
+        close = same_cov & (np.abs(n - ref.normal).max(axis=-1) < 1e-4)
+        assert close.mean() > 0.995, close.mean()
+        assert np.abs(d[close] - ref.depth[close]).max() < 2e-6
+        assert (np.abs(a[close].astype(int) - ref.albedo[close].astype(int)).max(axis=-1) <= 1).mean() > 0.999
+        assert np.array_equal(m[close], ref.material[close])
+        assert np.array_equal(e[close], ref.emission[close])
+
+
+def test_bvh_build_deterministic(rt_factory):
+    """Same input => bitwise identical BLAS and TLAS across builds and contexts."""
+    rng = np.random.default_rng(5)
+    nv, nt = 3000, 5000
+    verts = np.zeros((nv, 12), np.float32)
+    verts[:, :3] = rng.uniform(-3, 3, (nv, 3)).astype(np.float32)
+    verts[:100, :3] = verts[0, :3]  # duplicate positions => duplicate Morton codes
+    idx = rng.integers(0, nv, nt * 3).astype(np.uint32)
+    dumps, tdumps = [], []
+    for k in range(3):
+        rt = rt_factory()
+        b = rt.blas_create(verts, idx, stride=48)
+        b2 = rt.blas_create(verts, idx, stride=48)
+        d1, d2 = rt.blas_dump(b), rt.blas_dump(b2)
+        assert np.array_equal(d1, d2)
+        dumps.append(d1)
+        mats = [S.trs(rng2, 10.0 * i, (1, 1, 1)) for i, rng2 in enumerate(np.random.default_rng(1).uniform(-20, 20, (300, 3)))]
+        inst = rt.make_instances([b if i % 2 else b2 for i in range(300)], mats)
+        rt.tlas_build(inst, 300, 0)
+        tdumps.append(rt.tlas_dump())
+        rt.tlas_build(inst, 300, 0)
+        assert np.array_equal(tdumps[-1], rt.tlas_dump())
+    assert all(np.array_equal(dumps[0], d) for d in dumps[1:])
+    assert all(np.array_equal(tdumps[0], d) for d in tdumps[1:])
+
+
+def test_traversal_matches_exhaustive_random_mesh(rt_factory):
+    """Random triangle soup + rotated/scaled instances: closest-hit G-buffer coverage and any-hit masks
+    against the exhaustive oracle (no BVH on the oracle side)."""
+    rt = rt_factory()
+    rng = np.random.default_rng(21)
+    nv, nt = 600, 400
+    verts = np.zeros((nv, 12), np.float32)
+    verts[:, :3] = rng.uniform(-1, 1, (nv, 3)).astype(np.float32)
+    verts[:, 3:6] = (0, 1, 0)
+    base = rng.integers(0, nv - 3, nt)
+    idx = np.stack([base, base + 1, base + 2], 1).astype(np.uint32).reshape(-1)
+    sc = S.synthetic_scene(256, 144, grid=2, n_lights=2, light_samples=2, ao_samples=4, mixed_materials=False)
+    sc["meshes"].append((verts, idx))
+    for k in range(6):
+        m = S.trs((rng.uniform(-4, 4), rng.uniform(1, 3), rng.uniform(-4, 4)), rng.uniform(0, 360),
+                  (rng.uniform(0.5, 2), rng.uniform(0.2, 1.5), rng.uniform(0.5, 2)))
+        sc["instances"].append((1, m, 0))
+    compare_light(sc, 256, 144, 5, rt, exhaustive=True)
+
+
+def test_tlas_refit_matches_rebuild(rt_factory):
+    rt = rt_factory()
+    w, h = 256, 144
+    sc = S.synthetic_scene(w, h, grid=4, n_lights=2, light_samples=1, ao_samples=2)
+    world0 = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world0, sc["models"], len(sc["instances"]), [], w, h)
+    bn = S.blue_noise()
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+    blas, inst = S.make_rt_scene(rt, sc)
+    # move every instance, then refit
+    moved = [(m, (np.array(mat).reshape(4, 4) + np.array([[0, 0, 0, 0]] * 3 + [[0.3, 0.1 * (i % 3), -0.2, 0]], np.float32)).reshape(16), ci)
+             for i, (m, mat, ci) in enumerate(sc["instances"])]
+    sc2 = dict(sc, instances=moved)
+    inst2 = rt.make_instances([blas[m] for (m, _, _) in moved], [mat for (_, mat, _) in moved], [ci for (_, _, ci) in moved])
+    rt.tlas_build(inst2, len(moved), 1)
+    out_refit, sm1, am1, _ = run_light(rt, sc2, gb, 4, bn)
+    rt.tlas_build(inst2, len(moved), 0)
+    out_rebuild, sm2, am2, _ = run_light(rt, sc2, gb, 4, bn)
+    assert np.array_equal(sm1, sm2) and np.array_equal(am1, am2)
+    assert np.array_equal(out_refit, out_rebuild)
+    world = O.World(sc2["meshes"], moved)
+    rc, ref, sm, am, st = O.light_pass(sc2["scene"], gb, 4, bn, world, exhaustive=False, shadow_words=1, ao_words=1)
+    bad = popcount(sm1 ^ sm) + popcount(am1 ^ am)
+    assert 1.0 - bad / st.rays >= MASK_AGREE
+
+
+def test_empty_and_degenerate_inputs(rt_factory):
+    rt = rt_factory()
+    rt.resize(64, 32)
+    rt.set_blue_noise(S.blue_noise())
+    sc = S.synthetic_scene(64, 32, grid=2, n_lights=1)
+    # empty TLAS: nothing is occluded
+    rt.tlas_build(None, 0, 0)
+    gb = O.GBuffer(64, 32)
+    gb.normal[..., 1] = 1.0
+    gb.depth[:] = 0.999
+    gb.albedo[:] = 200
+    gb.material[:] = 128
+    out, sm, am, st = run_light(rt, sc, gb, 0, S.blue_noise())
+    assert popcount(sm) == 0 and popcount(am) == 0 and st.rays_occluded == 0
+    # empty mesh and single-triangle mesh
+    e = rt.blas_create(np.zeros((0, 12), np.float32), np.zeros(0, np.uint32), stride=48)
+    tri = np.zeros((3, 12), np.float32)
+    tri[:, :3] = [[-50, 2, -50], [50, 2, -50], [0, 2, 50]]
+    t = rt.blas_create(tri, np.array([0, 1, 2, 2], np.uint32), stride=48)  # trailing index ignored (count/3)
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    inst = rt.make_instances([e, t], [ident, ident])
+    rt.tlas_build(inst, 2, 0)
+    with pytest.raises(R.LuzError):
+        rt.blas_create(tri, np.array([0, 1, 3], np.uint32), stride=48)
+    with pytest.raises(R.LuzError):
+        rt.tlas_build(rt.make_instances([99], [ident]), 1, 0)
