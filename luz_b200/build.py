@@ -27,6 +27,10 @@ NVCC_FLAGS = [
     "-I", os.path.join(ROOT, "include"),
 ]
 CU_SOURCES = ["api.cu", "bvh_build.cu", "light_pass.cu", "taa.cu", "gbuffer.cu"]
+# The shading / resolve kernels restate GLSL that the oracle evaluates without FMA contraction; they are
+# built with -fmad=false so that implicit contraction cannot change results (ill-conditioned BRDF terms
+# amplify it), and use explicit fmaf() only where rounding is not part of parity (box tests).
+NO_FMAD = {"light_pass.cu", "taa.cu", "gbuffer.cu"}
 HOST_SOURCES = ["json.cpp", "scene.cpp", "gpu_scene.cpp", "deferred_renderer.cpp", "capi.cpp"]
 
 
@@ -66,7 +70,8 @@ def build_luzrt(force=False, verbose=False):
         o = os.path.join(BUILD, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _newer(o, [s] + hdrs):
-            jobs.append((NVCC_FLAGS_CMD(s, o), os.path.join(BUILD, src + ".log")))
+            jobs.append((NVCC_FLAGS_CMD(s, o, ["-fmad=false"] if src in NO_FMAD else []),
+                         os.path.join(BUILD, src + ".log")))
     if jobs:
         with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
             for out in ex.map(lambda j: _run(j[0], j[1]), jobs):
@@ -78,8 +83,8 @@ def build_luzrt(force=False, verbose=False):
     return lib
 
 
-def NVCC_FLAGS_CMD(src, obj):
-    return [NVCC] + NVCC_FLAGS + ["-c", src, "-o", obj]
+def NVCC_FLAGS_CMD(src, obj, extra=()):
+    return [NVCC] + NVCC_FLAGS + list(extra) + ["-c", src, "-o", obj]
 
 
 def build_luzhost(force=False):

@@ -50,8 +50,9 @@ __device__ __forceinline__ bool tri_test(const float4 p0, const float4 p1, const
     const float det = U + V + W;
     if (det == 0.0f) return false;
     // hit point relative to the origin = (U*A + V*B + W*C) / det; t = (P . d) / (d . d)
-    const float3 P = f3(U * A.x + V * B.x + W * C.x, U * A.y + V * B.y + W * C.y, U * A.z + V * B.z + W * C.z);
-    const float t = (dot3(P, d) * inv_dd) / det;
+    const float3 P = f3(fmaf(U, A.x, fmaf(V, B.x, W * C.x)), fmaf(U, A.y, fmaf(V, B.y, W * C.y)),
+                        fmaf(U, A.z, fmaf(V, B.z, W * C.z)));
+    const float t = (fmaf(P.x, d.x, fmaf(P.y, d.y, P.z * d.z)) * inv_dd) / det;
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
     bu = U / det;
