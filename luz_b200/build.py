@@ -31,7 +31,7 @@ CU_SOURCES = ["api.cu", "bvh_build.cu", "light_pass.cu", "taa.cu", "gbuffer.cu"]
 # built with -fmad=false so that implicit contraction cannot change results (ill-conditioned BRDF terms
 # amplify it), and use explicit fmaf() only where rounding is not part of parity (box tests).
 NO_FMAD = {"light_pass.cu", "taa.cu", "gbuffer.cu"}
-HOST_SOURCES = ["json.cpp", "scene.cpp", "gpu_scene.cpp", "deferred_renderer.cpp", "capi.cpp"]
+HOST_SOURCES = ["json.cpp", "scene.cpp", "gpu_scene.cpp", "capi.cpp"]
 
 
 def _newer(target, deps):
@@ -94,7 +94,8 @@ def build_luzhost(force=False):
     lib = os.path.join(PKG, "libluzhost.so")
     if force or _newer(lib, srcs + _headers(HOST)):
         _run([HOST_CXX, "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wall", "-Wno-unused-function",
-              "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-o", lib] + srcs + ["-ldl"])
+              "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-o", lib] + srcs +
+             ["-L", PKG, "-lluzrt", "-Wl,-rpath,$ORIGIN", "-ldl"])
     return lib
 
 
