@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""bench.py -- Mrays/s (shadow + AO any-hit rays) and ms/frame of the lighting pass.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3] [--impl ours|reference]
+
+A step is one frame of the hot path through the reference-facing host calls
+(GPUScene::UpdateResources[GPU] for animated configs, DeferredRenderer::LightPass, ::TAAPass
+[+ the NCCL frame gather when N > 1], ::SwapLightHistory) on synthetic data of BASELINE.json's shape.
+Default workload: configs[2] = "4K synthetic 10M-tri scene, 10k instances, 1 shadow ray/light + 16 AO
+spp" (the config the 4K metric and the north-star target are quoted on; it fits one GPU).
+N > 1: one process per GPU (torchrun), the frame is partitioned into H/N-row strips (strong scaling:
+the frame is fixed), each rank shades its strip + the two halo rows TAA reads, and one ncclAllGather
+assembles the resolved frame (next frame's TAA history) on every GPU.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's GLSL
+(oracle/, BVH2 traverser, OpenMP over all host cores) on a bounded sample of the same workload: the
+reference's Vulkan path cannot be built here (no Vulkan loader / glslang / lavapipe), which is the
+substitution BASELINE.json allows; the line says so.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (shadow+AO any-hit rays) of the deferred lighting + TAA frame"
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def setup_scene(args, rt, host_mod, scenes, tmp):
+    """Loads the workload as a Luz project through the host mirror and uploads its assets."""
+    path, bin_path, cfg = scenes.write_project(args.config, tmp, args.variant)
+    if args.width:
+        cfg["width"], cfg["height"] = args.width, args.height
+    app = host_mod.LuzHost(rt)
+    app.load_project(path, bin_path)
+    app.scene_settings(light_samples=cfg["light_samples"], ao_samples=cfg["ao_samples"])
+    return app, cfg
+
+
+def blue_noise(scenes):
+    p = os.path.join(ROOT, "tests", "golden", "blue_noise_256.rgba")
+    if os.path.exists(p):  # a 256x256 crop of the reference's own texture
+        return np.fromfile(p, dtype=np.uint8).reshape(256, 256, 4)
+    return scenes.synthetic_blue_noise(1024)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from luz_b200 import host as H
+    from luz_b200 import rt as R
+    from luz_b200 import scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("--gpus %d needs torchrun (one process per GPU)" % args.gpus)
+    if not torch.cuda.is_available():
+        sys.exit("bench.py: no CUDA device; the lighting path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    rt = R.LuzRT(device=local, rank=rank, world=world)
+    tmp = tempfile.mkdtemp(prefix="luzbench_r%d_" % rank)
+    app, cfg = setup_scene(args, rt, H, scenes, tmp)
+    W, Hh = cfg["width"], cfg["height"]
+    app.set_extent(W, Hh, create_images=True)
+    rt.set_blue_noise(blue_noise(scenes))
+    app.add_assets()
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.from_numpy(rt.comm_unique_id()))
+        dist.broadcast(idt, 0)
+        rt.comm_init(idt.cpu().numpy())
+
+    animate = cfg["animate"]
+    n_nodes = app.mesh_node_count()
+    base = [app.get_mesh_node_transform(i) for i in range(n_nodes)] if animate else None
+    base_pos = np.array([b[0] for b in base], np.float32) if animate else None
+    base_rot = np.array([b[1] for b in base], np.float32) if animate else None
+    tlas_flag = H.FRAME_TLAS_REFIT if animate == "refit" else 0
+
+    def step(frame, first=False):
+        if animate:
+            pos, rot = scenes.animate(args.config, frame, n_nodes, base_pos, base_rot)
+            if args.config == "c2":
+                app.set_mesh_node_transforms(1, rot=rot[1:])
+            else:
+                app.set_mesh_node_transforms(0, pos=pos)
+            # moving instances change primary visibility: the G-buffer producer runs too (not part of the metric)
+            app.render_frame(H.FRAME_OPAQUE | (0 if first else tlas_flag))
+        else:
+            app.render_frame(H.FRAME_OPAQUE if first else H.FRAME_NO_UPDATE)
+
+    stream = torch.cuda.ExternalStream(rt.stream(), device=torch.device("cuda", local))
+    # frame 0 builds the TLAS, produces the G-buffer on the device (input producer) and seeds the history
+    step(0, first=True)
+    rt.sync()
+
+    # one instrumented frame (outside the timed region): rays, nodes, triangles, instances per frame
+    rt.set_debug(R.DEBUG_STATS)
+    rt.light_pass(app.frame_count)
+    st = rt.read(R.STATS)
+    rt.set_debug(0)
+
+    for i in range(args.warmup):
+        step(1 + i)
+    rt.sync()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = rt.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(1 + args.warmup + i)
+    e1.record(stream)
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = rt.launch_count() - launches0
+    clocks = sampler.finish() if sampler else None
+
+    # per-kernel times, measured live with CUDA events on the launch stream (a few extra frames)
+    kt = {"light_ms": [], "taa_ms": [], "gather_ms": [], "tlas_ms": [], "gbuffer_ms": []}
+    for i in range(min(args.steps, 8)):
+        step(1 + args.warmup + args.steps + i)
+        t = rt.read(R.TIMINGS)
+        for k in kt:
+            kt[k].append(getattr(t, k))
+    kavg = {k: float(np.mean(v)) for k, v in kt.items()}
+
+    # ---- end to end through the C ABI with HOST buffers (G-buffer in, resolved frame out) ----
+    y0, y1 = rt.owned_rows()
+    e2e = None
+    if not args.no_e2e:
+        px = W * Hh
+        gbufs = {}
+        for sel, shape, dt in ((R.GBUF_ALBEDO, (Hh, W, 4), torch.uint8), (R.GBUF_NORMAL, (Hh, W, 4), torch.float32),
+                               (R.GBUF_MATERIAL, (Hh, W, 4), torch.uint8), (R.GBUF_EMISSION, (Hh, W, 4), torch.uint8),
+                               (R.GBUF_DEPTH, (Hh, W), torch.float32)):
+            t = torch.empty(shape, dtype=dt, pin_memory=True)
+            rt.read(sel, out=t.numpy())
+            gbufs[sel] = t
+        out_host = torch.empty((y1 - y0, W, 4), dtype=torch.float32, pin_memory=True)
+        sb = app.scene_block()
+        extra = app.extra_lights()
+        rows_up = (y1 - y0) + (2 if world > 1 else 0)
+
+        def e2e_step(frame):
+            rt.set_scene(sb, extra)
+            rt.set_gbuffer(gbufs[R.GBUF_ALBEDO].numpy(), gbufs[R.GBUF_NORMAL].numpy(), gbufs[R.GBUF_MATERIAL].numpy(),
+                           gbufs[R.GBUF_EMISSION].numpy(), gbufs[R.GBUF_DEPTH].numpy())
+            rt.light_pass(frame)
+            rt.taa_pass(True)
+            rt.gather()
+            rt.read_rows(R.IMG_LIGHT, y0, y1, out_host.numpy())
+            rt.swap_light_history()
+
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for i in range(n_e2e):
+            e2e_step(2 + i)
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        e2e = {"ms": e2e_ms, "h2d": rows_up * W * 32 + 31200, "d2h": (y1 - y0) * W * 16}
+
+    ms_per_step = total_ms / args.steps
+    vals = torch.tensor([ms_per_step, float(st.rays), e2e["ms"] if e2e else 0.0, kavg["light_ms"], kavg["taa_ms"],
+                         kavg["gather_ms"], kavg["tlas_ms"], float(st.nodes_visited), float(st.triangles_tested),
+                         float(st.instances_entered), float(st.lit_pixels)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    else:
+        mx, sm = vals, vals
+    mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
+    ms_per_step = float(mx[0])
+    rays_frame = float(sm[1])
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_sample(app, rt, R, W, Hh, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        hbm_peak, hbm_src = read_peaks()
+        l2_gbs = rt.probe_read_bandwidth(32 << 20, 200)
+        hbm_probe = rt.probe_read_bandwidth(4 << 30, 4)
+        light_ms, taa_ms = float(mx[3]), float(mx[4])
+        own_px = W * (y1 - y0)
+        trav_bytes = 80.0 * float(st.nodes_visited) + 48.0 * float(st.triangles_tested) + 64.0 * float(st.instances_entered)
+        shade_rows = (y1 - y0) + (2 if world > 1 else 0)
+        light_bytes = trav_bytes + 48.0 * W * shade_rows
+        out = {
+            "metric": METRIC, "value": rays_frame / ms_per_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px%s" % (
+                args.config, W, Hh, len(app.instances()), app.light_count(), cfg["light_samples"], cfg["ao_samples"],
+                (", TLAS %s per frame" % animate) if animate else ""),
+                "parallelism": "image strips x%d + ncclAllGather" % world if world > 1 else "1 GPU",
+                "rays_per_frame": rays_frame, "lit_pixels": float(sm[10]),
+                "l2_policy": "inputs larger than L2 (G-buffer + 3 light buffers = %.0f MB > 126 MB)" % (W * Hh * 80 / 1e6)},
+            "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6])},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_light_pass (fused shading + any-hit traversal)", "bound": "l2",
+                         "achieved": light_bytes / (light_ms * 1e6), "peak": l2_gbs, "unit": "GB/s",
+                         "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None, "traffic": None,
+                         "peak_source": "luzrt_probe_read_bandwidth, 32 MiB resident buffer, measured in this run",
+                         "bytes_per_ray": trav_bytes / max(float(st.rays), 1.0),
+                         "nodes_per_ray": float(st.nodes_visited) / max(float(st.rays), 1.0),
+                         "tris_per_ray": float(st.triangles_tested) / max(float(st.rays), 1.0),
+                         "instances_per_ray": float(st.instances_entered) / max(float(st.rays), 1.0),
+                         "grays_per_s": float(st.rays) / (light_ms * 1e6)},
+            "roofline_hbm": {"kernel": "k_taa", "bound": "hbm", "achieved": 52.0 * own_px / (taa_ms * 1e6),
+                             "peak": hbm_peak, "unit": "GB/s", "frac": 52.0 * own_px / (taa_ms * 1e6) / hbm_peak,
+                             "traffic": None, "peak_source": hbm_src, "hbm_read_probe_gbs": hbm_probe},
+        }
+        if e2e:
+            out["e2e"] = {"value": rays_frame / float(mx[2]) / 1e3, "unit": "Mrays/s", "ms_per_step": float(mx[2]),
+                          "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
+        if cpu_base:
+            out["cpu_baseline"] = cpu_base
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def oracle_world(app):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    return O, O.World(app.meshes(), app.instances())
+
+
+def cpu_baseline_sample(app, rt, R, W, Hh, budget_s=15.0):
+    """The oracle (CPU restatement, BVH2 traverser, all host cores) on a row sample of the same frame."""
+    O, world = oracle_world(app)
+    gb = O.GBuffer(W, Hh)
+    rt.read(R.GBUF_ALBEDO, out=gb.albedo)
+    rt.read(R.GBUF_NORMAL, out=gb.normal)
+    rt.read(R.GBUF_MATERIAL, out=gb.material)
+    rt.read(R.GBUF_EMISSION, out=gb.emission)
+    rt.read(R.GBUF_DEPTH, out=gb.depth)
+    return time_oracle_rows(O, world, app.scene_block(), app.extra_lights(), gb, W, Hh, budget_s, "port")
+
+
+def time_oracle_rows(O, world, sb, extra, gb, W, Hh, budget_s, kind):
+    from luz_b200 import scenes
+    bn = blue_noise(scenes)
+    mid = Hh // 2
+    t0 = time.perf_counter()
+    rc, _, _, _, st = O.light_pass(sb, gb, 0, bn, world, extra_lights=extra, exhaustive=False, rows=(mid, mid + 2))
+    dt = max(time.perf_counter() - t0, 1e-4)
+    rows = int(max(2, min(Hh, 2 * budget_s / dt)))
+    y0 = max(0, mid - rows // 2)
+    t0 = time.perf_counter()
+    rc, _, _, _, st = O.light_pass(sb, gb, 0, bn, world, extra_lights=extra, exhaustive=False, rows=(y0, y0 + rows))
+    dt = time.perf_counter() - t0
+    return {"value": st.rays / dt / 1e6, "unit": "Mrays/s", "cores": O.lib().orc_get_threads(), "kind": kind,
+            "sample": "light.frag restatement over rows [%d,%d) of the %dx%d frame (%d rays, %.1f s); "
+                      "CPU restatement, not lavapipe (no Vulkan/glslang in the image)" % (y0, y0 + rows, W, Hh, st.rays, dt),
+            "seconds": dt, "rays": int(st.rays)}
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's lighting path, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from luz_b200 import host as H
+    from luz_b200 import scenes
+    tmp = tempfile.mkdtemp(prefix="luzbench_ref_")
+    app, cfg = setup_scene(args, None, H, scenes, tmp)
+    W, Hh = cfg["width"], cfg["height"]
+    app.set_extent(W, Hh, create_images=False)
+    app.add_assets()
+    app.update_resources()
+    O, world = oracle_world(app)
+    sb, extra = app.scene_block(), app.extra_lights()
+    models, n_models = app.models()
+    # bounded sample: a band of rows in the middle of the frame; its G-buffer is produced by the oracle's
+    # own generator (input, untimed)
+    rows = max(2, args.ref_rows)
+    y0 = Hh // 2 - rows // 2
+    gb = O.gbuffer_pass(sb, world, models, n_models, app.textures(), W, Hh, exhaustive=False, rows=(y0, y0 + rows))
+    bn = blue_noise(scenes)
+    times, rays = [], 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        rc, light, _, _, st = O.light_pass(sb, gb, i, bn, world, extra_lights=extra, exhaustive=False, rows=(y0, y0 + rows))
+        O.taa_pass(sb, light, light, gb.depth, True, rows=(y0 + 1, y0 + rows - 1))
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            rays = st.rays
+    ms = float(np.mean(times)) * 1e3
+    val = rays / (ms * 1e3)
+    cores = O.lib().orc_get_threads()
+    sample = ("rows [%d,%d) of the %dx%d frame per step (%d rays); CPU restatement of light.frag/taa.comp with a BVH2 "
+              "traverser, not the Vulkan/lavapipe path (no Vulkan loader, glslang or lavapipe in the image)" % (
+                  y0, y0 + rows, W, Hh, rays))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px" % (
+            args.config, W, Hh, len(app.instances()), app.light_count(), cfg["light_samples"], cfg["ao_samples"]),
+            "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--variant", default=None, choices=[None, "unique"])
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--ref-rows", type=int, default=16)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

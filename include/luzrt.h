@@ -13,8 +13,9 @@
  *  - every call returns LUZRT_OK (0) or a negative luzrt_status; nothing aborts or throws.
  *    (The reference aborts via ASSERT/LOG_CRITICAL, Base.hpp:51-59; a library cannot.)
  *  - luzrt_last_error(ctx) gives the message for the last failing call on that ctx.
- *  - the caller owns every input buffer and may free it when the call returns (host inputs
- *    are staged through pinned memory and copied stream-ordered).
+ *  - the caller owns every input buffer.  Pageable host buffers are staged before the call returns
+ *    and may be freed at once; page-locked (cudaHostAlloc) buffers are read by DMA and must stay
+ *    valid until the next luzrt_sync / luzrt_read on the ctx (the usual CUDA rule).
  *  - calls are asynchronous and ordered on the ctx's CUDA stream, except luzrt_read,
  *    luzrt_sync, luzrt_blas_create (blocking like GPUScene::AddMesh's WaitQueue,
  *    GPUScene.cpp:132-137) and luzrt_create/destroy.
@@ -164,7 +165,8 @@ LUZRT_API int luzrt_set_scene(luzrt_ctx* ctx, const luzw_scene_block* scene_bloc
 
 /* The G-buffer the reference's opaque pass leaves in its attachments
  * (DeferredRenderer.cpp:176-238): full W*H images; NULL keeps the current contents.
- * src_is_device != 0: the pointers are device memory on this ctx's GPU. */
+ * src_is_device != 0: the pointers are device memory on this ctx's GPU.  The pointers always address
+ * full-frame images; a ctx of a multi-GPU frame copies only the rows it shades. */
 LUZRT_API int luzrt_set_gbuffer(luzrt_ctx* ctx, const void* albedo_rgba8, const void* normal_rgba32f,
                                 const void* material_rgba8, const void* emission_rgba8,
                                 const void* depth_f32, int src_is_device);
@@ -200,6 +202,14 @@ LUZRT_API int luzrt_swap_light_history(luzrt_ctx* ctx);
 
 /* Blocking read-back of one of the LUZRT_* selectors into host memory. */
 LUZRT_API int luzrt_read(luzrt_ctx* ctx, int which, void* dst, size_t bytes);
+/* Same for image selectors, restricted to rows [y0, y1): dst receives (y1-y0) packed rows. */
+LUZRT_API int luzrt_read_rows(luzrt_ctx* ctx, int which, uint32_t y0, uint32_t y1, void* dst, size_t bytes);
+/* The rows this ctx owns: [*y0, *y1) (the whole image when world == 1). */
+LUZRT_API int luzrt_owned_rows(luzrt_ctx* ctx, uint32_t* y0, uint32_t* y1);
+/* Measurement aid ("L2 peak must be measured by the builder"): streams a
+ * `bytes`-sized device buffer `iters` times with every SM and returns the achieved read GB/s.
+ * A buffer well below the 126 MB L2 measures L2 bandwidth, one far above it measures HBM. */
+LUZRT_API int luzrt_probe_read_bandwidth(luzrt_ctx* ctx, size_t bytes, int iters, double* out_gbs);
 /* Device pointer of an image selector (for hosts that keep working on the GPU). */
 LUZRT_API int luzrt_device_ptr(luzrt_ctx* ctx, int which, void** out_ptr, size_t* out_bytes);
 LUZRT_API int luzrt_sync(luzrt_ctx* ctx);

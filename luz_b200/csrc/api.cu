@@ -610,13 +610,27 @@ int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, cons
     if (!c) return LUZRT_E_INVALID;
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
     DeviceGuard g(c->device);
-    const size_t px = (size_t)c->w * c->h;
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (albedo) CU(c, cudaMemcpyAsync(c->albedo, albedo, px * 4, kind, c->stream));
-    if (normal) CU(c, cudaMemcpyAsync(c->normal, normal, px * 16, kind, c->stream));
-    if (material) CU(c, cudaMemcpyAsync(c->material, material, px * 4, kind, c->stream));
-    if (emission) CU(c, cudaMemcpyAsync(c->emission, emission, px * 4, kind, c->stream));
-    if (depth) CU(c, cudaMemcpyAsync(c->depth, depth, px * 4, kind, c->stream));
+    // row ranges this ctx shades: everything on one GPU, else own strip + one wrapped row on each side
+    uint32_t seg[3][2];
+    int nseg = 0;
+    if (c->world == 1 || c->y1 - c->y0 + 2 >= c->h) {
+        seg[nseg][0] = 0, seg[nseg++][1] = c->h;
+    } else {
+        const uint32_t lo = c->y0 == 0 ? 0 : c->y0 - 1, hi = c->y1 == c->h ? c->h : c->y1 + 1;
+        seg[nseg][0] = lo, seg[nseg++][1] = hi;
+        if (c->y0 == 0) seg[nseg][0] = c->h - 1, seg[nseg++][1] = c->h;
+        if (c->y1 == c->h) seg[nseg][0] = 0, seg[nseg++][1] = 1;
+    }
+    struct Plane { void* dst; const void* src; size_t bpp; } planes[5] = {
+        {c->albedo, albedo, 4}, {c->normal, normal, 16}, {c->material, material, 4},
+        {c->emission, emission, 4}, {c->depth, depth, 4}};
+    for (int s = 0; s < nseg; s++)
+        for (const Plane& p : planes) {
+            if (!p.src) continue;
+            const size_t off = (size_t)seg[s][0] * c->w * p.bpp, n = (size_t)(seg[s][1] - seg[s][0]) * c->w * p.bpp;
+            CU(c, cudaMemcpyAsync((char*)p.dst + off, (const char*)p.src + off, n, kind, c->stream));
+        }
     return LUZRT_OK;
 }
 
@@ -744,6 +758,8 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.ao_words = (uint32_t)c->ao_mask_words;
     a.stats = c->d_stats;
     a.lit_counters = c->d_lit;
+    a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
+    a.count_row_end = c->world == 1 ? c->h : 1u + (c->y1 - c->y0);
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
@@ -851,6 +867,57 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
     if (!src) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
     REQUIRE(c, bytes >= have, "destination buffer too small");
     CU(c, cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
+    return LUZRT_OK;
+}
+
+int luzrt_read_rows(luzrt_ctx* c, int which, uint32_t y0, uint32_t y1, void* dst, size_t bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, dst, "dst is null");
+    REQUIRE(c, y0 <= y1 && y1 <= c->h, "row range out of bounds");
+    DeviceGuard g(c->device);
+    size_t have = 0;
+    void* src = image_ptr(c, which, &have);
+    if (!src || !c->h) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
+    const size_t row = have / c->h, need = row * (y1 - y0);
+    REQUIRE(c, bytes >= need, "destination buffer too small");
+    CU(c, cudaMemcpyAsync(dst, (const char*)src + row * y0, need, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LUZRT_OK;
+}
+
+int luzrt_owned_rows(luzrt_ctx* c, uint32_t* y0, uint32_t* y1) {
+    if (!c || !y0 || !y1) return LUZRT_E_INVALID;
+    *y0 = c->y0;
+    *y1 = c->y1;
+    return LUZRT_OK;
+}
+
+int luzrt_probe_read_bandwidth(luzrt_ctx* c, size_t bytes, int iters, double* out_gbs) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, out_gbs && bytes >= (1u << 20) && iters > 0, "bad probe arguments");
+    DeviceGuard g(c->device);
+    void* buf = nullptr;
+    float* sink = nullptr;
+    CU(c, cudaMalloc(&buf, bytes));
+    CU(c, cudaMalloc(&sink, 4096));
+    CU(c, cudaMemsetAsync(buf, 1, bytes, c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaError_t err = launch_probe_read(c->stream, buf, bytes, 2, sink); // warm the cache
+    cudaEventRecord(e0, c->stream);
+    if (err == cudaSuccess) err = launch_probe_read(c->stream, buf, bytes, iters, sink);
+    cudaEventRecord(e1, c->stream);
+    c->launches += 2;
+    cudaStreamSynchronize(c->stream);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(sink);
+    if (err != cudaSuccess) return fail(c, LUZRT_E_CUDA, "probe kernel: %s", cudaGetErrorString(err));
+    *out_gbs = ms > 0.0f ? (double)bytes * iters / (ms * 1e6) : 0.0;
     return LUZRT_OK;
 }
 

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
     }
 
     // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
-    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit));
+    const unsigned int lit_warp =
+        __popc(__ballot_sync(0xFFFFFFFFu, lit && r >= a.count_row_begin && r < a.count_row_end));
     if (lane == 0 && lit_warp) atomicAdd(&s_lit, lit_warp);
     __syncthreads();
     if (threadIdx.x == 0 && s_lit)

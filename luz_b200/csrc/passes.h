@@ -26,6 +26,7 @@ struct LightArgs {
     uint32_t ao_words;
     DeviceStats* stats;
     unsigned long long* lit_counters; // 64 counters, 128 B apart
+    uint32_t count_row_begin, count_row_end; // rows (relative to row_start) whose lit pixels are counted
 };
 
 struct TaaArgs {
@@ -62,5 +63,7 @@ cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
 cudaError_t launch_compose_pass(cudaStream_t stream, const float4* light_in, uchar4* out_bgra, uint32_t width,
                                 uint32_t row_start, uint32_t row_count);
 cudaError_t launch_gbuffer_pass(cudaStream_t stream, const GbufferArgs& args);
+// bandwidth probe: every SM streams `bytes` of `buf` `iters` times with 128-bit loads
+cudaError_t launch_probe_read(cudaStream_t stream, const void* buf, size_t bytes, int iters, float* sink);
 
 } // namespace luz

@@ -189,7 +189,28 @@ __global__ void __launch_bounds__(256) k_compose(const float4* __restrict__ ligh
     out[first + i] = make_uchar4(unorm8(o[2]), unorm8(o[1]), unorm8(o[0]), 255); // BGRA8
 }
 
+__global__ void __launch_bounds__(512) k_probe_read(const uint4* __restrict__ buf, size_t n16, int iters,
+                                                    float* __restrict__ sink) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i); // L2 (not L1) is what is being measured
+            acc.x ^= v.x;
+            acc.y ^= v.y;
+            acc.z ^= v.z;
+            acc.w ^= v.w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[threadIdx.x] = 1.0f; // keep the loads alive
+}
+
 } // namespace
+
+cudaError_t launch_probe_read(cudaStream_t stream, const void* buf, size_t bytes, int iters, float* sink) {
+    k_probe_read<<<148 * 4, 512, 0, stream>>>(reinterpret_cast<const uint4*>(buf), bytes / 16, iters, sink);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args) {
     if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;

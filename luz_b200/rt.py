@@ -22,7 +22,8 @@ EXPORTS = [
     "luzrt_blas_destroy", "luzrt_blas_dump", "luzrt_tlas_dump", "luzrt_tlas_build", "luzrt_set_scene",
     "luzrt_set_gbuffer", "luzrt_gbuffer_pass", "luzrt_set_debug", "luzrt_light_pass", "luzrt_taa_pass",
     "luzrt_gather", "luzrt_compose_pass", "luzrt_swap_light_history", "luzrt_read", "luzrt_device_ptr",
-    "luzrt_sync", "luzrt_stream", "luzrt_launch_count",
+    "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_rows",
+    "luzrt_probe_read_bandwidth",
 ]
 
 
@@ -72,6 +73,9 @@ def load_library():
         "luzrt_sync": (i32, [vp]),
         "luzrt_stream": (i32, [vp, C.POINTER(u64)]),
         "luzrt_launch_count": (u64, [vp]),
+        "luzrt_read_rows": (i32, [vp, i32, u32, u32, vp, C.c_size_t]),
+        "luzrt_owned_rows": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "luzrt_probe_read_bandwidth": (i32, [vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -227,6 +231,20 @@ class LuzRT:
 
     def launch_count(self):
         return int(self.lib.luzrt_launch_count(self.h))
+
+    def owned_rows(self):
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(self.lib.luzrt_owned_rows(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def read_rows(self, which, y0, y1, out):
+        self._ck(self.lib.luzrt_read_rows(self.h, which, y0, y1, _ptr(out), out.nbytes))
+        return out
+
+    def probe_read_bandwidth(self, nbytes, iters):
+        g = C.c_double(0.0)
+        self._ck(self.lib.luzrt_probe_read_bandwidth(self.h, nbytes, iters, C.byref(g)))
+        return g.value
 
     def device_ptr(self, which):
         p, n = C.c_void_p(), C.c_size_t()

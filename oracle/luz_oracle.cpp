@@ -1029,10 +1029,10 @@ inline V3 normal_xform(const float* inv, V3 n) {
 
 int orc_gbuffer_pass(const luzw_scene_block* scene, const orc_world* world, const luzw_model_block* models,
                      uint32_t n_models, const orc_texture* textures, uint32_t n_textures, uint32_t width,
-                     uint32_t height, int exhaustive, orc_gbuffer* out) {
+                     uint32_t height, int exhaustive, uint32_t y0, uint32_t y1, orc_gbuffer* out) {
     int err = 0;
 #pragma omp parallel for schedule(dynamic, 2) ORC_NT
-    for (int64_t yy = 0; yy < (int64_t)height; yy++) {
+    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
         for (uint32_t x = 0; x < width; x++) {
             const size_t pix = (size_t)yy * width + x;
             const float u = ((float)x + 0.5f) / (float)width, v = ((float)yy + 0.5f) / (float)height;

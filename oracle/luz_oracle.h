@@ -89,10 +89,10 @@ int orc_taa_pass(const luzw_scene_block* scene, uint32_t width, uint32_t height,
 /* present.frag imageType 0 -> BGRA8. */
 int orc_compose_pass(uint32_t width, uint32_t height, const float* light_in, uint8_t* out_bgra8);
 
-/* opaque.vert/frag as primary visibility (input producer). */
+/* opaque.vert/frag as primary visibility (input producer), rows [y0, y1) of full-frame buffers. */
 int orc_gbuffer_pass(const luzw_scene_block* scene, const orc_world* world, const luzw_model_block* models,
                      uint32_t n_models, const orc_texture* textures, uint32_t n_textures, uint32_t width,
-                     uint32_t height, int exhaustive, orc_gbuffer* out);
+                     uint32_t height, int exhaustive, uint32_t y0, uint32_t y1, orc_gbuffer* out);
 
 /* Small exported helpers for known-answer tests. */
 void orc_blue_noise_sample(const uint8_t* bn, uint32_t bn_w, uint32_t bn_h, uint32_t px, uint32_t py, int i,

@@ -59,7 +59,7 @@ def lib():
         L.orc_compose_pass.restype = i32
         L.orc_compose_pass.argtypes = [u32, u32, vp, vp]
         L.orc_gbuffer_pass.restype = i32
-        L.orc_gbuffer_pass.argtypes = [vp, vp, vp, u32, vp, u32, u32, u32, i32, vp]
+        L.orc_gbuffer_pass.argtypes = [vp, vp, vp, u32, vp, u32, u32, u32, i32, u32, u32, vp]
         L.orc_blue_noise_sample.argtypes = [vp, u32, u32, u32, u32, i32, u32, vp]
         L.orc_depth_to_world.argtypes = [vp, C.c_float, C.c_float, C.c_float, vp]
         L.orc_mitchell.restype = C.c_float
@@ -145,8 +145,9 @@ class GBuffer:
                           self.emission.ctypes.data, self.depth.ctypes.data)
 
 
-def gbuffer_pass(scene, world, models, n_models, textures, w, h, exhaustive=False):
+def gbuffer_pass(scene, world, models, n_models, textures, w, h, exhaustive=False, rows=None):
     gb = GBuffer(w, h)
+    y0, y1 = rows if rows else (0, h)
     tex = (OrcTexture * max(len(textures), 1))()
     keep = []
     for i, t in enumerate(textures):
@@ -155,7 +156,7 @@ def gbuffer_pass(scene, world, models, n_models, textures, w, h, exhaustive=Fals
         tex[i] = OrcTexture(t.ctypes.data, t.shape[1], t.shape[0])
     g = gb.c()
     rc = lib().orc_gbuffer_pass(_p(scene), world.h, _p(models), n_models, _p(tex), len(textures), w, h,
-                                1 if exhaustive else 0, _p(g))
+                                1 if exhaustive else 0, y0, y1, _p(g))
     assert rc == 0
     return gb
 
