@@ -680,7 +680,7 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     }
     GbufferArgs a{};
     a.fc = c->fc;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, 0x3F800000u};
     a.inst_meta = c->d_meta;
     a.blas_attr = c->d_blas_attr;
     a.models = c->d_models;
@@ -744,7 +744,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.blue_noise = c->blue_noise;
     a.lights = c->d_lights;
     a.out = c->lightA;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, 0x3F800000u};
     if (c->world == 1) {
         a.row_start = 0;
         a.row_count = c->h;

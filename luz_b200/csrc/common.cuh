@@ -55,6 +55,7 @@ struct BlasAttr { // per-BLAS vertex attributes kept for the G-buffer pass
 struct TraceScene {
     const WideNode* tlas_nodes;
     const InstanceRec* instances;
+    uint32_t one_bits; // 0x3F800000, deliberately a run-time value (see traverse.cuh)
 };
 
 // compact light record staged in shared memory (first 64 bytes of a LightBlock)

@@ -6,6 +6,8 @@
 // (TraceAORays), :137-169 (EvaluateShadow), :57-75 (samplers) and :17-49 (BRDF) of the reference;
 // launched where DeferredRenderer::LightPass (DeferredRenderer.cpp:324-345) draws its quad.
 // One warp shades an 8x4 pixel tile; the light list is staged in shared memory.
+#include <cstdlib>
+
 #include "passes.h"
 #include "traverse.cuh"
 
@@ -44,11 +46,10 @@ __device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughne
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
-template <bool MASKS, bool STATS>
-__global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
+template <bool MASKS, bool STATS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
-    __shared__ unsigned int s_lit;
 
     const FrameConst& fc = a.fc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,7 +63,6 @@ __global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
         y = (uint32_t)yy;
     }
     const size_t pix = (size_t)y * fc.width + x;
-    if (threadIdx.x == 0) s_lit = 0;
 
     // ---- G-buffer fetch (light.frag:172-176; texel loads) ----
     float3 N = f3(0.0f, 0.0f, 0.0f);
@@ -109,68 +109,103 @@ __global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
     }
     uint32_t shadow_bit = 0;
 
-    for (int base = 0; base < fc.num_lights; base += kLightChunk) {
-        const int chunk = min(kLightChunk, fc.num_lights - base);
+    // One loop over "ray sources": the lights of the scene (shadow rays, light.frag:192-227) followed by
+    // one pseudo source for ambient occlusion (light.frag:229-231), so that the kernel contains a single
+    // inlined copy of the traversal (instruction-cache footprint) and every ray goes through one call site.
+    float rayTracedAo = 1.0f;
+    const int n_sources = fc.num_lights + 1;
+    for (int base = 0; base < n_sources; base += kLightChunk) {
+        const int chunk = min(kLightChunk, n_sources - base);
+        const int chunk_lights = min(chunk, fc.num_lights - base);
         __syncthreads();
-        for (int k = threadIdx.x; k < chunk * 4; k += blockDim.x)
+        for (int k = threadIdx.x; k < chunk_lights * 4; k += blockDim.x)
             reinterpret_cast<float4*>(s_lights)[k] = __ldg(reinterpret_cast<const float4*>(a.lights + base) + k);
         __syncthreads();
         if (!lit) continue;
         for (int li = 0; li < chunk; li++) {
-            const LightRec L4 = s_lights[li];
-            const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
-            const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
-            const float3 Lvec = lpos - fragPos;
-            const float dist = length3(Lvec);
-            float3 L = Lvec / dist; // normalize(L_)
-            float attenuation = 1.0f;
-            if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
-                L = normalize3(-ldir);
-            } else if (L4.type == LUZW_LIGHT_SPOT) {
-                attenuation = 1.0f / (dist * dist);
-                const float theta = dot3(L, normalize3(-ldir));
-                const float epsilon = L4.position_inner.w - L4.direction_outer.w;
-                attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
-            } else if (L4.type == LUZW_LIGHT_POINT) {
-                attenuation = 1.0f / (dist * dist);
+            const bool is_ao = base + li == fc.num_lights;
+            // ---- per-source set-up ----
+            float3 O, L = f3(0.0f, 0.0f, 0.0f), T, B, C; // ray origin, light dir, sampling frame (T, B, C)
+            float attenuation = 1.0f, radius = 0.0f, tMinRay, tMaxRay;
+            float4 lcolor = f4(0.0f, 0.0f, 0.0f, 0.0f);
+            int n_samples;
+            bool directional_or_shadowless = false;
+            if (is_ao) { // TraceAORays (light.frag:111-135)
+                O = fragPos + N * (camDist * 0.01f);
+                T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+                B = cross3(N, T);
+                C = N;
+                tMinRay = fc.ao_min;
+                tMaxRay = fc.ao_max;
+                n_samples = fc.ao_num_samples;
+            } else {
+                const LightRec L4 = s_lights[li];
+                const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
+                const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
+                const float3 Lvec = lpos - fragPos;
+                const float dist = length3(Lvec);
+                L = Lvec / dist; // normalize(L_)
+                if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
+                    L = normalize3(-ldir);
+                } else if (L4.type == LUZW_LIGHT_SPOT) {
+                    attenuation = 1.0f / (dist * dist);
+                    const float theta = dot3(L, normalize3(-ldir));
+                    const float epsilon = L4.position_inner.w - L4.direction_outer.w;
+                    attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
+                } else if (L4.type == LUZW_LIGHT_POINT) {
+                    attenuation = 1.0f / (dist * dist);
+                }
+                lcolor = L4.color_intensity;
+                radius = L4.radius;
+                // EvaluateShadow (light.frag:137-169) + TraceShadowRay set-up (:86-98)
+                O = fragPos + N * fmaxf(camDist * 0.01f, 0.05f);
+                C = (L4.type == LUZW_LIGHT_DIRECTIONAL) ? ldir * dot3(ldir, L) * dist : L * dist;
+                T = normalize3(cross3(C, f3(0.0f, 1.0f, 0.0f)));
+                B = normalize3(cross3(T, C));
+                tMinRay = 0.001f;
+                tMaxRay = length3(C);
+                n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
+                directional_or_shadowless = fc.shadow_type != LUZW_SHADOW_RAYTRACING;
             }
-            // ---- EvaluateShadow (light.frag:137-169) ----
-            float shadowFactor = 1.0f;
-            if (fc.shadow_type == LUZW_SHADOW_RAYTRACING) {
-                const float numSamples = (float)L4.num_shadow_samples;
-                shadowFactor = 0.0f;
-                if (numSamples != 0.0f) { // TraceShadowRay :86-109
-                    const float shadowBias = fmaxf(camDist * 0.01f, 0.05f);
-                    const float3 O = fragPos + N * shadowBias;
-                    const float3 Lr = (L4.type == LUZW_LIGHT_DIRECTIONAL) ? ldir * dot3(ldir, L) * dist : L * dist;
-                    const float3 T = normalize3(cross3(Lr, f3(0.0f, 1.0f, 0.0f)));
-                    const float3 B = normalize3(cross3(T, Lr));
-                    const float tMax = length3(Lr);
-                    float numShadows = 0.0f;
-                    for (int i = 0; (float)i < numSamples; i++) {
-                        const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
-                        const float pointRadius = L4.radius * sqrtf(rng.x);
-                        const float pointAngle = rng.y * 2.0f * kPI;
-                        float sn, cs;
-                        sincosf(pointAngle, &sn, &cs);
-                        const float dx = pointRadius * cs, dy = pointRadius * sn;
-                        const float3 dir = normalize3(Lr + dx * T + dy * B);
-                        n_rays++;
-                        if (trace_ray<false, STATS>(a.scene, O, dir, 0.001f, tMax, nullptr, &st)) {
-                            numShadows += 1.0f;
-                            n_occl++;
-                            if (MASKS) {
-                                const uint32_t b = shadow_bit + (uint32_t)i;
-                                smask[b >> 5] |= 1u << (b & 31u);
-                            }
+            // ---- the rays of this source ----
+            float hits = 0.0f;
+            for (int i = 0; i < n_samples; i++) {
+                const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
+                float sn, cs;
+                float3 dir;
+                if (is_ao) { // HemisphereSample (light.frag:63-69)
+                    const float rr = sqrtf(rng.x);
+                    sincosf(6.283f * rng.y, &sn, &cs);
+                    dir = T * (rr * cs) + B * (rr * sn) + C * sqrtf(fmaxf(0.0f, 1.0f - rng.x));
+                } else { // DiskSample (light.frag:57-61)
+                    const float pointRadius = radius * sqrtf(rng.x);
+                    sincosf(rng.y * 2.0f * kPI, &sn, &cs);
+                    dir = normalize3(C + (pointRadius * cs) * T + (pointRadius * sn) * B);
+                }
+                n_rays++;
+                if (trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st)) {
+                    hits += 1.0f;
+                    n_occl++;
+                    if (MASKS) {
+                        if (is_ao) {
+                            amask[i >> 5] |= 1u << (i & 31);
+                        } else {
+                            const uint32_t b = shadow_bit + (uint32_t)i;
+                            smask[b >> 5] |= 1u << (b & 31u);
                         }
                     }
-                    shadowFactor = numShadows / numSamples;
                 }
-                shadow_bit += (uint32_t)max(L4.num_shadow_samples, 0);
             }
-            const float3 lcol = f3(L4.color_intensity.x, L4.color_intensity.y, L4.color_intensity.z);
-            const float3 radiance = lcol * L4.color_intensity.w * attenuation * (1.0f - shadowFactor);
+            if (is_ao) {
+                if (n_samples != 0) rayTracedAo = ((float)n_samples - hits) / (float)n_samples; // ao / aoNumSamples
+                continue;
+            }
+            shadow_bit += (uint32_t)max(n_samples, 0);
+            // shadow factor: RT with samples -> occluded fraction; RT with 0 samples -> 0; otherwise 1 (:166-168)
+            float shadowFactor = directional_or_shadowless ? 1.0f : 0.0f;
+            if (n_samples > 0) shadowFactor = hits / (float)n_samples;
+            const float3 lcol = f3(lcolor.x, lcolor.y, lcolor.z);
+            const float3 radiance = lcol * lcolor.w * attenuation * (1.0f - shadowFactor);
 
             const float3 H = normalize3(V + L);
             const float NDF = distribution_ggx(N, H, roughness);
@@ -188,32 +223,6 @@ __global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
     }
 
     if (lit) {
-        // ---- TraceAORays (light.frag:111-135, :229-231) ----
-        float rayTracedAo = 1.0f;
-        if (fc.ao_num_samples != 0) {
-            const float aoBias = camDist * 0.01f;
-            const float3 P = fragPos + N * aoBias;
-            const float3 tangent = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
-            const float3 bitangent = cross3(N, tangent);
-            float ao = 0.0f;
-            for (int i = 0; i < fc.ao_num_samples; i++) {
-                const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
-                const float rr = sqrtf(rng.x);
-                const float theta = 6.283f * rng.y;
-                float sn, cs;
-                sincosf(theta, &sn, &cs);
-                const float hx = rr * cs, hy = rr * sn, hz = sqrtf(fmaxf(0.0f, 1.0f - rng.x));
-                const float3 dir = tangent * hx + bitangent * hy + N * hz;
-                n_rays++;
-                if (!trace_ray<false, STATS>(a.scene, P, dir, fc.ao_min, fc.ao_max, nullptr, &st)) {
-                    ao += 1.0f;
-                } else {
-                    n_occl++;
-                    if (MASKS) amask[i >> 5] |= 1u << (i & 31);
-                }
-            }
-            rayTracedAo = ao / (float)fc.ao_num_samples;
-        }
         const float3 emission = f3((float)e8.x / 255.0f, (float)e8.y / 255.0f, (float)e8.z / 255.0f);
         const float3 ambient = ambientLight * albedo * occlusion * rayTracedAo;
         const float3 color = ambient + Lo + emission;
@@ -221,12 +230,12 @@ __global__ void __launch_bounds__(128) k_light_pass(const LightArgs a) {
     }
 
     // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
+    // (no CTA-wide barrier here: warps of a tile finish at very different times)
     const unsigned int lit_warp =
         __popc(__ballot_sync(0xFFFFFFFFu, lit && r >= a.count_row_begin && r < a.count_row_end));
-    if (lane == 0 && lit_warp) atomicAdd(&s_lit, lit_warp);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_lit)
-        atomicAdd(a.lit_counters + 16 * ((blockIdx.x + blockIdx.y * 7u) & 63u), (unsigned long long)s_lit);
+    if (lane == 0 && lit_warp)
+        atomicAdd(a.lit_counters + 16 * ((blockIdx.x * 4u + blockIdx.y * 29u + warp) & 63u),
+                  (unsigned long long)lit_warp);
     if (STATS) {
         unsigned long long vals[5] = {n_rays, st.nodes, st.tris, st.insts, n_occl};
 #pragma unroll
@@ -251,14 +260,28 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool m
     if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;
     const dim3 grid((args.fc.width + 15) / 16, (args.row_count + 7) / 8);
     const size_t smem = sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk));
+    // resident CTAs per SM the production variant is compiled for (register cap = 65536 / (128 * n));
+    // LUZRT_LIGHT_MINB selects among the compiled variants for tuning runs
+    static const int minb = [] {
+        const char* e = getenv("LUZRT_LIGHT_MINB");
+        return e ? atoi(e) : 4;
+    }();
     if (masks && stats)
-        k_light_pass<true, true><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<true, true, 4><<<grid, 128, smem, stream>>>(args);
     else if (masks)
-        k_light_pass<true, false><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<true, false, 4><<<grid, 128, smem, stream>>>(args);
     else if (stats)
-        k_light_pass<false, true><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, true, 4><<<grid, 128, smem, stream>>>(args);
+    else if (minb == 3)
+        k_light_pass<false, false, 3><<<grid, 128, smem, stream>>>(args);
+    else if (minb == 5)
+        k_light_pass<false, false, 5><<<grid, 128, smem, stream>>>(args);
+    else if (minb == 6)
+        k_light_pass<false, false, 6><<<grid, 128, smem, stream>>>(args);
+    else if (minb == 8)
+        k_light_pass<false, false, 8><<<grid, 128, smem, stream>>>(args);
     else
-        k_light_pass<false, false><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 4><<<grid, 128, smem, stream>>>(args);
     return cudaGetLastError();
 }
 

@@ -18,11 +18,14 @@ __device__ __forceinline__ int wrapi(int i, int n) {
     return r < 0 ? r + n : r;
 }
 
+// REPEAT addressing for coordinates known to lie in [-n, 2n): no integer division
+__device__ __forceinline__ int wrap1(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
+
 struct Img {
     const float4* p;
     int w, h;
-    __device__ __forceinline__ float4 texel(int x, int y) const {
-        return __ldg(p + (size_t)wrapi(y, h) * w + wrapi(x, w));
+    __device__ __forceinline__ float4 texel(int x, int y) const { // x, y within one period of the image
+        return __ldg(p + (size_t)wrap1(y, h) * w + wrap1(x, w));
     }
 };
 
@@ -60,13 +63,13 @@ __global__ void __launch_bounds__(256) k_taa(const TaaArgs a) {
     // find_closest_3x3: first strict minimum in row-major order
     const float ddx = fabsf(1.0f / sw), ddy = fabsf(1.0f / sh);
     int bi = -1, bj = -1;
-    float dminz = __ldg(a.depth + (size_t)wrapi(y - 1, H) * W + wrapi(x - 1, W));
+    float dminz = __ldg(a.depth + (size_t)wrap1(y - 1, H) * W + wrap1(x - 1, W));
 #pragma unroll
     for (int j = -1; j <= 1; j++)
 #pragma unroll
         for (int i = -1; i <= 1; i++) {
             if (i == -1 && j == -1) continue;
-            const float z = __ldg(a.depth + (size_t)wrapi(y + j, H) * W + wrapi(x + i, W));
+            const float z = __ldg(a.depth + (size_t)wrap1(y + j, H) * W + wrap1(x + i, W));
             if (dminz > z) {
                 bi = i;
                 bj = j;
@@ -88,7 +91,6 @@ __global__ void __launch_bounds__(256) k_taa(const TaaArgs a) {
         mvy = ((curNDC.y - fc.jitter[1]) - (prevNDC.y - fc.prev_jitter[1])) * 0.5f;
     }
     const float hu = su - mvx, hv = sv - mvy;
-    float4 historySample = bilinear(hist, hu, hv);
 
     // get_neighbor_3x3
     const float4 ctl = light.texel(x - 1, y - 1), ctc = light.texel(x, y - 1), ctr = light.texel(x + 1, y - 1);
@@ -135,6 +137,9 @@ __global__ void __launch_bounds__(256) k_taa(const TaaArgs a) {
         *dst = sourceSample;
         return;
     }
+    // texture(lightHistory, historyUv): the shader fetches it before the bounds test (taa.comp:281) but only
+    // uses it past this point; here 0 <= uv <= 1, so the four taps are within one period of the image
+    float4 historySample = bilinear(hist, hu, hv);
     { // clip_aabb(cmin.rgb, cmax.rgb, clamp(cavg, cmin, cmax), history)
         const float4 p = f4(clampf(cavg.x, cmin.x, cmax.x), clampf(cavg.y, cmin.y, cmax.y),
                             clampf(cavg.z, cmin.z, cmax.z), clampf(cavg.w, cmin.w, cmax.w));

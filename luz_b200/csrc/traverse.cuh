@@ -60,43 +60,73 @@ __device__ __forceinline__ bool tri_test(const float4 p0, const float4 p1, const
     return true;
 }
 
-// Intersects the ray with the eight quantised child boxes; returns the hit mask in the
-// "bits 31..24 = internal children by slot, bits 23..0 = leaf primitives" form.
-__device__ __forceinline__ uint32_t intersect_node(const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3,
-                                                   const uint4 n4, const float3 o, const float3 idir,
-                                                   const float tmin, const float tmax) {
+// Ray vs the eight quantised child boxes of a wide node.
+//
+// Dequantisation without integer->float conversions (I2F runs on the quarter-rate XU pipe and was
+// the top stall in the first ncu profile, profiles/r1_light_pass_v0.md): one PRMT drops the byte q
+// into the mantissa of 1.0f, giving v = 1 + q*2^-15 exactly, and one FFMA evaluates
+//     t = q*adj + o  ==  v*A + (o - A),   A = adj * 2^15.
+// Rounding (o - A) costs at most |adj|*2^-9 (1/512 of a grid cell); both planes are pushed outwards
+// by |adj|*2^-8 and the far plane is scaled by (1 + 2^-21) so the test stays conservative.
+__device__ __forceinline__ float q_as_float(uint32_t packed, uint32_t one_bits, uint32_t selector) {
+    return __uint_as_float(__byte_perm(packed, one_bits, selector));
+}
+
+// Returns the 8-bit mask of child slots whose box the ray overlaps in [tmin, tmax].
+__device__ __forceinline__ uint32_t intersect_node(const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4,
+                                                   const float3 o, const float3 idir, const float tmin,
+                                                   const float tmax, const uint32_t one_bits) {
+    const float kFar = 1.0000005f;
+    // per-axis constants
     const float adjx = __uint_as_float((n0.w & 0xFFu) << 23) * idir.x;
     const float adjy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idir.y;
     const float adjz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
-    const float ox = (__uint_as_float(n0.x) - o.x) * idir.x;
-    const float oy = (__uint_as_float(n0.y) - o.y) * idir.y;
-    const float oz = (__uint_as_float(n0.z) - o.z) * idir.z;
-    uint32_t hitmask = 0;
+    const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
+    const float Bx = (__uint_as_float(n0.x) - o.x) * idir.x - Ax;
+    const float By = (__uint_as_float(n0.y) - o.y) * idir.y - Ay;
+    const float Bz = (__uint_as_float(n0.z) - o.z) * idir.z - Az;
+    const float px = fabsf(adjx) * 0.00390625f, py = fabsf(adjy) * 0.00390625f, pz = fabsf(adjz) * 0.00390625f;
+    const float Bnx = Bx - px, Bny = By - py, Bnz = Bz - pz;
+    const float Afx = Ax * kFar, Afy = Ay * kFar, Afz = Az * kFar;
+    const float Bfx = fmaf(Bx, kFar, px), Bfy = fmaf(By, kFar, py), Bfz = fmaf(Bz, kFar, pz);
+    const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
+    uint32_t slots = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = half ? n1.w : n1.z;
         const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
         const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
-        const uint32_t nx = idir.x < 0.0f ? hix : lox, fx = idir.x < 0.0f ? lox : hix;
-        const uint32_t ny = idir.y < 0.0f ? hiy : loy, fy = idir.y < 0.0f ? loy : hiy;
-        const uint32_t nz = idir.z < 0.0f ? hiz : loz, fz = idir.z < 0.0f ? loz : hiz;
+        const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
+        const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
+        const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float tnx = fmaf((float)((nx >> (8 * j)) & 0xFFu), adjx, ox);
-            const float tny = fmaf((float)((ny >> (8 * j)) & 0xFFu), adjy, oy);
-            const float tnz = fmaf((float)((nz >> (8 * j)) & 0xFFu), adjz, oz);
-            const float tfx = fmaf((float)((fx >> (8 * j)) & 0xFFu), adjx, ox);
-            const float tfy = fmaf((float)((fy >> (8 * j)) & 0xFFu), adjy, oy);
-            const float tfz = fmaf((float)((fz >> (8 * j)) & 0xFFu), adjz, oz);
+            const uint32_t sel = 0x7604u | ((uint32_t)j << 4); // bytes: [3F][80][q_j][00]
+            const float tnx = fmaf(q_as_float(nx, one_bits, sel), Ax, Bnx);
+            const float tny = fmaf(q_as_float(ny, one_bits, sel), Ay, Bny);
+            const float tnz = fmaf(q_as_float(nz, one_bits, sel), Az, Bnz);
+            const float tfx = fmaf(q_as_float(fx, one_bits, sel), Afx, Bfx);
+            const float tfy = fmaf(q_as_float(fy, one_bits, sel), Afy, Bfy);
+            const float tfz = fmaf(q_as_float(fz, one_bits, sel), Afz, Bfz);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (cmin <= cmax * 1.0000005f) {
-                const uint32_t meta = (meta4 >> (8 * j)) & 0xFFu;
-                hitmask |= (meta >> 5) << (meta & 31u);
-            }
+            if (cmin <= cmax) slots |= 1u << (4 * half + j);
         }
     }
-    return hitmask;
+    return slots;
+}
+
+// Expands the hit leaf slots of a node into the primitive bit field (bits 23..0).  Empty slots carry
+// an inverted box and never hit; internal slots are masked out by the caller.
+__device__ __forceinline__ uint32_t leaf_bits(uint32_t leaf_slots, const uint32_t meta_lo, const uint32_t meta_hi) {
+    uint32_t bits = 0;
+    while (leaf_slots) {
+        const int s = __ffs(leaf_slots) - 1;
+        leaf_slots &= leaf_slots - 1u;
+        const uint32_t m4 = s < 4 ? meta_lo : meta_hi;
+        const uint32_t meta = (m4 >> (8 * (s & 3))) & 0xFFu;
+        bits |= (meta >> 5) << (meta & 31u);
+    }
+    return bits;
 }
 
 // CLOSEST == false: any-hit, returns true at the first committed intersection.
@@ -110,6 +140,10 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
         return false;
     if (wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f) return false;
 
+    // 0x3F800000 comes in as a kernel parameter: PRMT then takes it straight from the constant bank and keeps
+    // its selector as an immediate (with a literal, ptxas puts the selector in a register and re-creates it
+    // with a MOV in front of every PRMT: profiles/r1_light_pass_v1.md)
+    const uint32_t one_bits = sc.one_bits;
     uint2 stack[LUZ_STACK_SIZE];
     int sp = 0;
     int inst_sp = -1; // stack height at which the current instance was entered, -1 = in the TLAS
@@ -126,7 +160,9 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     uint2 tgroup = make_uint2(0u, 0u);
 
     while (true) {
-        if (ngroup.y > 0x00FFFFFFu) {
+        // node phase: every lane keeps descending until it holds primitives to test (or runs out of nodes), so
+        // that the expensive leaf work below is entered by as many lanes of the warp together as possible
+        while (ngroup.y > 0x00FFFFFFu && tgroup.y == 0u) {
             const uint32_t hits = ngroup.y;
             const uint32_t imask = hits & 0xFFu;
             const int bit = 31 - __clz(hits);
@@ -138,12 +174,10 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
                         n4 = __ldg(np + 4);
             if (STATS) st->nodes++;
-            const uint32_t hm = intersect_node(n0, n1, n2, n3, n4, o, idir, tmin, tmax);
-            ngroup = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-            tgroup = make_uint2(n1.y, hm & 0x00FFFFFFu);
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
+            const uint32_t slots = intersect_node(n0, n2, n3, n4, o, idir, tmin, tmax, one_bits);
+            const uint32_t node_imask = n0.w >> 24;
+            ngroup = make_uint2(n1.x, ((slots & node_imask) << 24) | node_imask);
+            tgroup = make_uint2(n1.y, leaf_bits(slots & ~node_imask, n1.z, n1.w));
         }
 
         while (tgroup.y != 0u) {
@@ -203,7 +237,13 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 nodes = sc.tlas_nodes;
             }
             if (sp == 0) break;
-            ngroup = stack[--sp];
+            const uint2 e = stack[--sp];
+            if (e.y > 0x00FFFFFFu) {
+                ngroup = e;
+            } else { // a postponed primitive group
+                tgroup = e;
+                ngroup = make_uint2(0u, 0u);
+            }
         }
     }
     return found;
