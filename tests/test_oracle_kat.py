@@ -1,0 +1,234 @@
+"""Known-answer tests that pin the CPU oracle (oracle/luz_oracle.cpp) without a GPU.
+
+The reference ships no tests or golden outputs for this path and its GLSL cannot be
+executed here, so these answers are derived by hand / with independent float64 numpy from the reference's
+shader text (file:line cited per test)."""
+import ctypes as C
+import math
+
+import numpy as np
+
+import oracle_api as O
+import scene_util as S
+from luz_b200 import wire
+
+
+def test_mitchell_weights_match_utils_glsl():
+    # utils.glsl:9-15 with B = C = 1/3: y = (6-2B) x^3 - (6-2B-3C... evaluated literally as the shader writes it.
+    # taa.comp samples it at distances 0, 1, sqrt(2): SURVEY 8(a) a14 quotes weights 1, 2, ~7.418
+    L = O.lib()
+    assert L.orc_mitchell(0.0) == 1.0
+    assert abs(L.orc_mitchell(1.0) - 2.0) < 1e-6
+    assert abs(L.orc_mitchell(math.sqrt(2.0)) - 7.418) < 2e-3
+
+
+def test_blue_noise_sample_light_frag_71_75():
+    bn = S.blue_noise()
+    L = O.lib()
+    out = np.zeros(2, np.float32)
+    GOLDEN = np.float32(2.118033988749895)  # LuzCommon.h:12 (sic)
+    for (px, py, i, frame) in [(0, 0, 0, 0), (5, 9, 3, 7), (300, 511, 15, 127), (17, 3, 63, 32767), (1279, 719, 255, 129)]:
+        L.orc_blue_noise_sample(bn.ctypes.data, 256, 256, px, py, i, frame, out.ctypes.data)
+        texel = bn[py % 256, px % 256].astype(np.float32) / np.float32(255.0)
+        k = np.float32(128 * i + frame % 128)
+        off = np.float32(GOLDEN * k)
+        exp = [np.float32(texel[c] + off) - np.floor(np.float32(texel[c] + off)) for c in range(2)]
+        assert out[0] == np.float32(exp[0]) and out[1] == np.float32(exp[1]), (px, py, i, frame)
+        assert 0.0 <= out[0] < 1.0 and 0.0 <= out[1] < 1.0
+
+
+def test_tri_test_known_answers():
+    L = O.lib()
+    f3 = lambda *v: np.array(v, np.float32)
+    v0, v1, v2 = f3(0, 0, 0), f3(1, 0, 0), f3(0, 1, 0)
+    t = C.c_float(0)
+
+    def hit(o, d, tmin, tmax):
+        oo, dd = f3(*o), f3(*d)  # keep the arrays alive across the call
+        return L.orc_tri_test(v0.ctypes.data, v1.ctypes.data, v2.ctypes.data, oo.ctypes.data, dd.ctypes.data,
+                              tmin, tmax, C.byref(t))
+
+    assert hit((0.25, 0.25, 1), (0, 0, -1), 0.0, 10.0) == 1 and abs(t.value - 1.0) < 1e-6
+    assert hit((0.25, 0.25, -1), (0, 0, 1), 0.0, 10.0) == 1          # two-sided (VulkanWrapper.cpp:1119)
+    assert hit((0.25, 0.25, 1), (0, 0, -1), 0.0, 0.5) == 0           # beyond tmax
+    assert hit((0.25, 0.25, 1), (0, 0, -1), 1.5, 10.0) == 0          # before tmin
+    assert hit((0.75, 0.75, 1), (0, 0, -1), 0.0, 10.0) == 0          # outside the hypotenuse
+    assert hit((0.25, 0.25, 1), (1, 0, 0), 0.0, 10.0) == 0           # parallel
+    # t is parametric along the un-normalised direction (light.frag:116-126 AO rays)
+    assert hit((0.25, 0.25, 1), (0, 0, -4), 0.0, 10.0) == 1 and abs(t.value - 0.25) < 1e-6
+    assert hit((0.25, 0.25, 1), (0, 0, -4), 0.0, 0.2) == 0
+    # shared edge of two triangles is watertight: a ray exactly through the edge hits at least one
+    w0, w1, w2 = f3(1, 0, 0), f3(1, 1, 0), f3(0, 1, 0)
+    for s in np.linspace(0.01, 0.99, 23):
+        o = f3(1 - s, s, 1.0)
+        d = f3(0.0, 0.0, -1.0)
+        a = L.orc_tri_test(v0.ctypes.data, v1.ctypes.data, v2.ctypes.data, o.ctypes.data, d.ctypes.data, 0.0, 10.0, C.byref(t))
+        b = L.orc_tri_test(w0.ctypes.data, w1.ctypes.data, w2.ctypes.data, o.ctypes.data, d.ctypes.data, 0.0, 10.0, C.byref(t))
+        assert a or b
+
+
+def test_depth_to_world_inverts_view_proj():
+    # utils.glsl:1-7: world = inverseView * (inverseProj * clip / w); projecting back with the reference's own
+    # viewProj (golden, from the compiled reference host code) must return the clip coordinates
+    sc = S.default_scene(frame=3)
+    sb = sc["scene"]
+    vp = np.array(list(sb.view_proj), np.float64).reshape(4, 4).T
+    out = np.zeros(3, np.float32)
+    for (u, v, d) in [(0.5, 0.5, 0.9), (0.1, 0.8, 0.99), (0.93, 0.07, 0.999)]:
+        O.lib().orc_depth_to_world(C.byref(sb), u, v, d, out.ctypes.data)
+        clip = vp @ np.array([out[0], out[1], out[2], 1.0])
+        ndc = clip[:3] / clip[3]
+        assert abs(ndc[0] - (2 * u - 1)) < 2e-4 and abs(ndc[1] - (2 * v - 1)) < 2e-4 and abs(ndc[2] - d) < 2e-4
+
+
+def test_default_scene_visibility_known_answers():
+    # a ray from under the unit cube at y=1 toward the slab must be occluded; the slab's top is
+    # at y = 0.00847 (scale 8.47e-3 of a +-1 cube), the unit cube spans y in [0, 2]
+    sc = S.default_scene()
+    w = O.World(sc["meshes"], sc["instances"])
+    o = np.array([[0.0, 3.0, 0.0], [0.0, 3.0, 0.0], [6.0, 0.5, 6.0], [6.0, 0.5, 6.0], [0.0, 0.5, 0.0]], np.float32)
+    d = np.array([[0, -1, 0], [0, 1, 0], [0, -1, 0], [0, 1, 0], [0, 1, 0]], np.float32)
+    hit = w.trace_any(o, d, 1e-3, 100.0, exhaustive=True)
+    # above the cube looking down: hit (cube top at y=2); looking up: miss; beside the cube above the slab
+    # looking down: hit (slab); up: miss; inside the cube looking up: hit its top from below (two-sided)
+    assert hit.tolist() == [1, 0, 1, 0, 1]
+    t, inst, prim = w.trace_closest(o[:1], d[:1], 1e-3, 100.0, exhaustive=True)
+    assert abs(t[0] - 1.0) < 1e-5
+    # tmax shorter than the distance: miss
+    assert w.trace_any(o[:1], d[:1], 1e-3, 0.5, exhaustive=True).tolist() == [0]
+
+
+def test_bvh2_traverser_equals_exhaustive_on_default_scene():
+    # the timed CPU baseline uses the oracle's BVH2 traverser; validate it against the exhaustive truth (8d)
+    sc = S.default_scene()
+    w = O.World(sc["meshes"], sc["instances"])
+    rng = np.random.default_rng(5)
+    n = 20000
+    o = rng.uniform(-9, 9, (n, 3)).astype(np.float32)
+    o[:, 1] = rng.uniform(-1, 6, n)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    tmax = rng.uniform(0.1, 30.0, n).astype(np.float32)
+    a = w.trace_any(o, d, 1e-3, tmax, exhaustive=True)
+    b = w.trace_any(o, d, 1e-3, tmax, exhaustive=False)
+    assert np.array_equal(a, b)
+    assert 0.05 < a.mean() < 0.95
+
+
+def _numpy_shade_pixel(sb, gb, x, y, w, h, shadow, ao):
+    """Independent float64 restatement of light.frag:171-235 for ONE pixel with given shadow/AO factors."""
+    albedo = (gb.albedo[y, x, :3].astype(np.float64) / 255.0) ** 2.2
+    N = gb.normal[y, x, :3].astype(np.float64)
+    rough, metal, occl = gb.material[y, x, :3].astype(np.float64) / 255.0
+    emis = gb.emission[y, x, :3].astype(np.float64) / 255.0
+    depth = float(gb.depth[y, x])
+    ip = np.array(list(sb.inverse_proj), np.float64).reshape(4, 4).T
+    iv = np.array(list(sb.inverse_view), np.float64).reshape(4, 4).T
+    clip = np.array([(x + 0.5) / w * 2 - 1, (y + 0.5) / h * 2 - 1, depth, 1.0])
+    view = ip @ clip
+    view /= view[3]
+    P = (iv @ view)[:3]
+    cam = np.array(list(sb.cam_pos), np.float64)
+    V = (cam - P) / np.linalg.norm(cam - P)
+    F0 = 0.04 * (1 - metal) + albedo * metal
+    Lo = np.zeros(3)
+    for i in range(sb.num_lights):
+        l = sb.lights[i]
+        lpos = np.array(list(l.position), np.float64)
+        Lv = lpos - P
+        dist = np.linalg.norm(Lv)
+        L = Lv / dist
+        att = 1.0
+        if l.type == wire.LIGHT_POINT:
+            att = 1.0 / dist ** 2
+        elif l.type == wire.LIGHT_DIRECTIONAL:
+            L = -np.array(list(l.direction), np.float64)
+            L /= np.linalg.norm(L)
+        rad = np.array(list(l.color), np.float64) * l.intensity * att * (1.0 - shadow[i])
+        H = (V + L) / np.linalg.norm(V + L)
+        a2 = (rough * rough) ** 2
+        NdotH = max(N @ H, 0.0)
+        NDF = a2 / (math.pi * (NdotH * NdotH * (a2 - 1) + 1) ** 2)
+        k = (rough + 1) ** 2 / 8
+        NdotV, NdotL = max(N @ V, 0.0), max(N @ L, 0.0)
+        G = (NdotV / (NdotV * (1 - k) + k)) * (NdotL / (NdotL * (1 - k) + k))
+        F = F0 + (1 - F0) * min(max(1 - min(max(H @ V, 0), 1), 0), 1) ** 5
+        spec = NDF * G * F / (4 * NdotV * NdotL + 1e-4)
+        kD = (1 - F) * (1 - metal)
+        Lo += (kD * albedo / math.pi + spec) * rad * NdotL
+    amb = np.array(list(sb.ambient_light_color), np.float64) * sb.ambient_light_intensity * albedo * occl * ao
+    return amb + Lo + emis
+
+
+def test_light_pass_pixel_known_answers_default_scene():
+    """Oracle light pass vs an independent float64 evaluation of light.frag for individual pixels of C1
+    (assets/default.luz, one point light): with no rays (numShadowSamples = 0, aoNumSamples = 0) the shader is
+    closed-form (light.frag:87-89, :112-114)."""
+    w, h = 320, 180
+    sc = S.default_scene(frame=0, light_samples=0, ao_samples=0, w=1280, h=720)
+    world = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h, exhaustive=True)
+    bn = S.blue_noise()
+    rc, out, _, _, st = O.light_pass(sc["scene"], gb, 0, bn, world, exhaustive=True)
+    assert rc == 0 and st.rays == 0
+    lit = np.argwhere(np.linalg.norm(gb.normal[:, :, :3], axis=2) > 0)
+    assert len(lit) > 1000
+    rng = np.random.default_rng(3)
+    for (y, x) in lit[rng.choice(len(lit), 40, replace=False)]:
+        exp = _numpy_shade_pixel(sc["scene"], gb, x, y, w, h, shadow=[0.0] * 64, ao=1.0)
+        assert np.allclose(out[y, x, :3], exp, rtol=2e-4, atol=2e-5), (x, y, out[y, x], exp)
+        assert out[y, x, 3] == 1.0
+    # background pixels: ambientColor * ambientIntensity, alpha 1 (light.frag:178-181)
+    bg = np.argwhere(np.linalg.norm(gb.normal[:, :, :3], axis=2) == 0)
+    assert len(bg) > 100
+    amb = np.array(list(sc["scene"].ambient_light_color), np.float32) * np.float32(sc["scene"].ambient_light_intensity)
+    y, x = bg[0]
+    assert np.array_equal(out[y, x], np.array([amb[0], amb[1], amb[2], 1.0], np.float32))
+
+
+def test_shadow_type_semantics_light_frag_141_168():
+    """shadowType 0 (disabled) returns 1.0 = fully shadowed: only ambient*AO + emission remain."""
+    w, h = 160, 90
+    sc = S.default_scene(frame=0, light_samples=1, ao_samples=0)
+    world = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h, exhaustive=True)
+    sc["scene"].shadow_type = 0
+    rc, out, _, _, st = O.light_pass(sc["scene"], gb, 0, S.blue_noise(), world, exhaustive=True)
+    assert rc == 0 and st.rays == 0
+    lit = np.argwhere(np.linalg.norm(gb.normal[:, :, :3], axis=2) > 0)
+    y, x = lit[len(lit) // 2]
+    exp = _numpy_shade_pixel(sc["scene"], gb, x, y, w, h, shadow=[1.0] * 64, ao=1.0)
+    assert np.allclose(out[y, x, :3], exp, rtol=2e-4, atol=2e-5)
+
+
+def test_ray_count_is_lights_times_samples_plus_ao():
+    # exactly numLights*numShadowSamples + aoNumSamples rays per lit pixel, none for background
+    w, h = 96, 54
+    sc = S.synthetic_scene(w, h, grid=3, n_lights=3, light_samples=2, ao_samples=5)
+    world = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), [], w, h, exhaustive=True)
+    rc, out, sm, am, st = O.light_pass(sc["scene"], gb, 9, S.blue_noise(), world, exhaustive=True, shadow_words=1, ao_words=1)
+    lit = int((np.linalg.norm(gb.normal[:, :, :3], axis=2) > 0).sum())
+    assert rc == 0 and st.lit_pixels == lit and st.rays == lit * (3 * 2 + 5)
+    assert int(sm.max()) < (1 << 6) and int(am.max()) < (1 << 5)
+
+
+def test_taa_first_frame_identity_and_wrap():
+    """taa.comp with history == input, zero motion: the result stays inside the 3x3 neighbourhood box
+    (clip_aabb, :121-143) and a constant image is a fixed point."""
+    w, h = 64, 48
+    sc = S.synthetic_scene(w, h, grid=2, n_lights=1, light_samples=0, ao_samples=0)
+    sb = sc["scene"]
+    for i in range(16):
+        sb.prev_view_proj[i] = sb.view_proj[i]
+    sb.prev_jitter[0], sb.prev_jitter[1] = sb.jitter[0], sb.jitter[1]
+    const = np.full((h, w, 4), 0.37, np.float32)
+    depth = np.full((h, w), 0.9, np.float32)
+    out = O.taa_pass(sb, const, const, depth, True)
+    assert np.allclose(out, 0.37, atol=1e-6)
+    rng = np.random.default_rng(2)
+    img = rng.uniform(0, 2, (h, w, 4)).astype(np.float32)
+    out = O.taa_pass(sb, img, img, depth, False)
+    # neighbourhood min/max with REPEAT wrap at the borders (VulkanWrapper.cpp:2433-2437)
+    pad = np.pad(img, ((1, 1), (1, 1), (0, 0)), mode="wrap")
+    stack = np.stack([pad[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)])
+    assert (out <= stack.max(0) + 1e-5).all() and (out >= stack.min(0) - 1e-5).all()
