@@ -98,6 +98,7 @@ struct luzrt_ctx {
     InstanceIn* d_inst_in = nullptr;
     InstanceRec *d_recs_in = nullptr, *d_recs = nullptr;
     InstanceMeta *d_meta_in = nullptr, *d_meta = nullptr;
+    float4* d_inst_boxes = nullptr; // 2 per instance, TLAS leaf order
     size_t inst_cap = 0;
     uint32_t n_inst = 0;
     std::vector<luzrt_blas> last_blas;
@@ -267,7 +268,7 @@ void luzrt_destroy(luzrt_ctx* c) {
     for (auto& t : c->textures)
         if (t.data) cudaFree(t.data);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
-                    c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models,
+                    c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
                     c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -516,12 +517,13 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     const size_t cap_need = std::max<uint32_t>(count, 1);
     if (c->inst_cap < cap_need) {
         CU(c, cudaStreamSynchronize(c->stream));
-        void* olds[] = {c->d_inst_in, c->d_recs_in, c->d_recs, c->d_meta_in, c->d_meta};
+        void* olds[] = {c->d_inst_in, c->d_recs_in, c->d_recs, c->d_meta_in, c->d_meta, c->d_inst_boxes};
         for (void* p : olds)
             if (p) cudaFree(p);
         c->d_inst_in = nullptr;
         c->d_recs_in = c->d_recs = nullptr;
         c->d_meta_in = c->d_meta = nullptr;
+        c->d_inst_boxes = nullptr;
         c->inst_cap = 0;
         const size_t n = cap_need + cap_need / 2;
         CU(c, cudaMalloc(&c->d_inst_in, n * sizeof(InstanceIn)));
@@ -529,6 +531,7 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
         CU(c, cudaMalloc(&c->d_recs, n * sizeof(InstanceRec)));
         CU(c, cudaMalloc(&c->d_meta_in, n * sizeof(InstanceMeta)));
         CU(c, cudaMalloc(&c->d_meta, n * sizeof(InstanceMeta)));
+        CU(c, cudaMalloc(&c->d_inst_boxes, n * 2 * sizeof(float4)));
         c->inst_cap = n;
     }
     int rc;
@@ -544,7 +547,8 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     } else {
         CU(c, build_wide_bvh(c->stream, c->scratch, c->d_boxes, count, 1, c->tlas, &c->launches));
     }
-    CU(c, launch_instance_gather(c->stream, c->d_recs_in, c->d_meta_in, c->tlas.prim_order, count, c->d_recs, c->d_meta));
+    CU(c, launch_instance_gather(c->stream, c->d_recs_in, c->d_meta_in, c->d_boxes, c->tlas.prim_order, count, c->d_recs,
+                                 c->d_meta, c->d_inst_boxes));
     c->launches += count ? 1 : 0;
     ev_end(c, EV_TLAS);
     c->n_inst = count;
@@ -680,7 +684,7 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     }
     GbufferArgs a{};
     a.fc = c->fc;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, 0x3F800000u};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u};
     a.inst_meta = c->d_meta;
     a.blas_attr = c->d_blas_attr;
     a.models = c->d_models;
@@ -744,7 +748,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.blue_noise = c->blue_noise;
     a.lights = c->d_lights;
     a.out = c->lightA;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, 0x3F800000u};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u};
     if (c->world == 1) {
         a.row_start = 0;
         a.row_count = c->h;

@@ -66,8 +66,8 @@ cudaError_t launch_instance_prepare(cudaStream_t stream, const InstanceIn* d_in,
                                     InstanceRec* d_recs_in_order, InstanceMeta* d_meta_in_order);
 // Permutes records into TLAS leaf order.
 cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceRec* d_recs_in, const InstanceMeta* d_meta_in,
-                                   const uint32_t* d_prim_order, uint32_t n, InstanceRec* d_recs_out,
-                                   InstanceMeta* d_meta_out);
+                                   const BoxF* d_boxes_in, const uint32_t* d_prim_order, uint32_t n,
+                                   InstanceRec* d_recs_out, InstanceMeta* d_meta_out, float4* d_boxes_out);
 // Boxes permuted into leaf order (for refit).
 cudaError_t launch_box_gather(cudaStream_t stream, const BoxF* d_in, const uint32_t* d_prim_order, uint32_t n,
                               BoxF* d_out);

@@ -614,13 +614,17 @@ __global__ void k_instance_prepare(const InstanceIn* __restrict__ in, uint32_t n
 }
 
 __global__ void k_instance_gather(const InstanceRec* __restrict__ rin, const InstanceMeta* __restrict__ min_,
-                                  const uint32_t* __restrict__ order, uint32_t n, InstanceRec* __restrict__ rout,
-                                  InstanceMeta* __restrict__ mout) {
+                                  const BoxF* __restrict__ bin, const uint32_t* __restrict__ order, uint32_t n,
+                                  InstanceRec* __restrict__ rout, InstanceMeta* __restrict__ mout,
+                                  float4* __restrict__ bout) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t src = order[k];
     rout[k] = rin[src];
     mout[k] = min_[src];
+    const BoxF b = bin[src];
+    bout[2 * k] = make_float4(b.lox, b.loy, b.loz, 0.0f);
+    bout[2 * k + 1] = make_float4(b.hix, b.hiy, b.hiz, 0.0f);
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -825,8 +829,9 @@ cudaError_t launch_instance_prepare(cudaStream_t stream, const InstanceIn* in, u
     return cudaGetLastError();
 }
 cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceRec* rin, const InstanceMeta* min_,
-                                   const uint32_t* order, uint32_t n, InstanceRec* rout, InstanceMeta* mout) {
-    if (n) k_instance_gather<<<div_up(n, 128), 128, 0, stream>>>(rin, min_, order, n, rout, mout);
+                                   const BoxF* bin, const uint32_t* order, uint32_t n, InstanceRec* rout,
+                                   InstanceMeta* mout, float4* bout) {
+    if (n) k_instance_gather<<<div_up(n, 128), 128, 0, stream>>>(rin, min_, bin, order, n, rout, mout, bout);
     return cudaGetLastError();
 }
 

@@ -55,6 +55,7 @@ struct BlasAttr { // per-BLAS vertex attributes kept for the G-buffer pass
 struct TraceScene {
     const WideNode* tlas_nodes;
     const InstanceRec* instances;
+    const float4* inst_boxes; // world boxes of the instances, TLAS leaf order: [2i] = lo.xyz, [2i+1] = hi.xyz
     uint32_t one_bits; // 0x3F800000, deliberately a run-time value (see traverse.cuh)
 };
 

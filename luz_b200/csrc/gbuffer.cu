@@ -68,12 +68,13 @@ __global__ void __launch_bounds__(128) k_gbuffer(const GbufferArgs a) {
 
     float tmin = 0.0f;
     bool have = false;
+    uint2 stack[LUZ_STACK_SIZE];
     float4 albedo = f4(0, 0, 0, 0), emission = f4(0, 0, 0, 0);
     float roughness = 0.0f, metallic = 0.0f, occl = 1.0f, depth = 1.0f;
     float3 N = f3(0, 0, 0);
     for (int iter = 0; iter < 16 && !have; iter++) {
         HitInfo h;
-        if (!trace_ray<true, false>(a.scene, pn, d, tmin, 1.0f, &h, nullptr)) break;
+        if (!trace_ray<true, false>(a.scene, pn, d, tmin, 1.0f, &h, nullptr, stack)) break;
         const InstanceMeta im = a.inst_meta[h.inst];
         if (im.custom_index >= a.n_models) break;
         const luzw_model_block& mb = a.models[im.custom_index];

@@ -18,6 +18,8 @@ namespace {
 constexpr float kPI = 3.14159265359f;              // LuzCommon.h:11
 constexpr float kGoldenRatio = 2.118033988749895f; // LuzCommon.h:12 (sic)
 constexpr int kLightChunk = 256;
+constexpr int kMinCandSamples = 6; // below this the one TLAS walk per pixel does not pay for itself (C2: 4 spp)
+constexpr int kMaxCand = 8; // instances an AO candidate list can hold per pixel before falling back to the root descent
 
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 
@@ -50,6 +52,8 @@ template <bool MASKS, bool STATS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
+    // per-thread AO candidate lists, [k][thread] so that a warp's accesses are conflict free
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw + a.cand_offset) + threadIdx.x;
 
     const FrameConst& fc = a.fc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -97,6 +101,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
     const float ggxV = geometry_schlick_ggx(NdotV, roughness);
 
     float3 Lo = f3(0.0f, 0.0f, 0.0f);
+    uint2 stack[LUZ_STACK_SIZE];
     LocalStats st = {0, 0, 0};
     uint32_t n_rays = 0, n_occl = 0;
     uint32_t* smask = nullptr;
@@ -129,6 +134,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
             float attenuation = 1.0f, radius = 0.0f, tMinRay, tMaxRay;
             float4 lcolor = f4(0.0f, 0.0f, 0.0f, 0.0f);
             int n_samples;
+            int n_cand = -1; // < 0: rays descend from the TLAS root
             bool directional_or_shadowless = false;
             if (is_ao) { // TraceAORays (light.frag:111-135)
                 O = fragPos + N * (camDist * 0.01f);
@@ -138,6 +144,16 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                 tMinRay = fc.ao_min;
                 tMaxRay = fc.ao_max;
                 n_samples = fc.ao_num_samples;
+                if (n_samples >= kMinCandSamples) {
+                    // every AO ray of this pixel stays inside O +- aoMax * |dir| per axis, and
+                    // |dir_k| = |T_k h.x + B_k h.y + N_k h.z| <= sqrt(T_k^2 + B_k^2 + N_k^2) * |h| with |h| = 1 (+ rounding):
+                    // one TLAS walk with that box replaces the TLAS levels of all aoNumSamples rays
+                    const float m = fabsf(tMaxRay) * 1.001f;
+                    const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
+                                          m * sqrtf(T.y * T.y + B.y * B.y + C.y * C.y) + 1e-6f,
+                                          m * sqrtf(T.z * T.z + B.z * B.z + C.z * C.z) + 1e-6f);
+                    n_cand = collect_instances<STATS>(a.scene, O - ext, O + ext, s_cand, 128, kMaxCand, stack, &st);
+                }
             } else {
                 const LightRec L4 = s_lights[li];
                 const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
@@ -183,7 +199,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                     dir = normalize3(C + (pointRadius * cs) * T + (pointRadius * sn) * B);
                 }
                 n_rays++;
-                if (trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st)) {
+                if (trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand)) {
                     hits += 1.0f;
                     n_occl++;
                     if (MASKS) {
@@ -259,7 +275,9 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats) {
     if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;
     const dim3 grid((args.fc.width + 15) / 16, (args.row_count + 7) / 8);
-    const size_t smem = sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk));
+    LightArgs a2 = args;
+    a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
+    const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
     // resident CTAs per SM the production variant is compiled for (register cap = 65536 / (128 * n));
     // LUZRT_LIGHT_MINB selects among the compiled variants for tuning runs
     static const int minb = [] {
@@ -267,21 +285,21 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool m
         return e ? atoi(e) : 4;
     }();
     if (masks && stats)
-        k_light_pass<true, true, 4><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<true, true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (masks)
-        k_light_pass<true, false, 4><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<true, false, 4><<<grid, 128, smem, stream>>>(a2);
     else if (stats)
-        k_light_pass<false, true, 4><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 3)
-        k_light_pass<false, false, 3><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 3><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 5)
-        k_light_pass<false, false, 5><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 5><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 6)
-        k_light_pass<false, false, 6><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 6><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 8)
-        k_light_pass<false, false, 8><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 8><<<grid, 128, smem, stream>>>(a2);
     else
-        k_light_pass<false, false, 4><<<grid, 128, smem, stream>>>(args);
+        k_light_pass<false, false, 4><<<grid, 128, smem, stream>>>(a2);
     return cudaGetLastError();
 }
 
