@@ -764,6 +764,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.lit_counters = c->d_lit;
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + (c->y1 - c->y0);
+    a.rays_per_pixel = c->rays_per_lit_pixel;
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));

@@ -27,7 +27,8 @@ struct LightArgs {
     DeviceStats* stats;
     unsigned long long* lit_counters; // 64 counters, 128 B apart
     uint32_t count_row_begin, count_row_end; // rows (relative to row_start) whose lit pixels are counted
-    uint32_t cand_offset;                    // byte offset of the AO candidate lists in dynamic shared memory
+    uint32_t node_repeat;                    // TRACE: keep visiting nodes while at least this many lanes can
+    uint32_t rays_per_pixel;                 // sum of numShadowSamples over the lights (ray-traced shadows) + aoNumSamples
 };
 
 struct TaaArgs {
