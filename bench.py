@@ -8,9 +8,9 @@ A step is one frame of the hot path through the reference-facing host calls
 [+ the NCCL frame gather when N > 1], ::SwapLightHistory) on synthetic data of BASELINE.json's shape.
 Default workload: configs[2] = "4K synthetic 10M-tri scene, 10k instances, 1 shadow ray/light + 16 AO
 spp" (the config the 4K metric and the north-star target are quoted on; it fits one GPU).
-N > 1: one process per GPU (torchrun), the frame is partitioned into H/N-row strips (strong scaling:
-the frame is fixed), each rank shades its strip + the two halo rows TAA reads, and one ncclAllGather
-assembles the resolved frame (next frame's TAA history) on every GPU.
+N > 1: one process per GPU (torchrun), the frame is cut into bands of ~54 rows dealt round-robin to the
+ranks (strong scaling: the frame is fixed), each rank shades its bands + the halo rows TAA reads, and one
+ncclAllGather assembles the resolved frame (next frame's TAA history) on every GPU.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's GLSL
 (oracle/, BVH2 traverser, OpenMP over all host cores) on a bounded sample of the same workload: the
@@ -101,6 +101,7 @@ def run_ours(args):
     from luz_b200 import host as H
     from luz_b200 import rt as R
     from luz_b200 import scenes
+    from luz_b200 import strips
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -177,6 +178,7 @@ def run_ours(args):
     e0.record(stream)
     for i in range(args.steps):
         step(1 + args.warmup + i)
+    rt.device_ptr(R.IMG_LIGHT)  # orders the ctx stream after the last frame's gather (it runs on its own stream)
     e1.record(stream)
     barrier()
     total_ms = e0.elapsed_time(e1)
@@ -193,7 +195,7 @@ def run_ours(args):
     kavg = {k: float(np.mean(v)) for k, v in kt.items()}
 
     # ---- end to end through the C ABI with HOST buffers (G-buffer in, resolved frame out) ----
-    y0, y1 = rt.owned_rows()
+    own_rows = Hh // world
     e2e = None
     if not args.no_e2e:
         px = W * Hh
@@ -204,10 +206,9 @@ def run_ours(args):
             t = torch.empty(shape, dtype=dt, pin_memory=True)
             rt.read(sel, out=t.numpy())
             gbufs[sel] = t
-        out_host = torch.empty((y1 - y0, W, 4), dtype=torch.float32, pin_memory=True)
+        out_host = torch.empty((own_rows, W, 4), dtype=torch.float32, pin_memory=True)
         sb = app.scene_block()
         extra = app.extra_lights()
-        rows_up = (y1 - y0) + (2 if world > 1 else 0)
 
         def e2e_step(frame):
             rt.set_scene(sb, extra)
@@ -216,7 +217,7 @@ def run_ours(args):
             rt.light_pass(frame)
             rt.taa_pass(True)
             rt.gather()
-            rt.read_rows(R.IMG_LIGHT, y0, y1, out_host.numpy())
+            rt.read_owned(R.IMG_LIGHT, out_host.numpy())
             rt.swap_light_history()
 
         for i in range(2):
@@ -226,9 +227,10 @@ def run_ours(args):
         n_e2e = max(3, min(args.steps, 10))
         for i in range(n_e2e):
             e2e_step(2 + i)
+        rt.sync()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        e2e = {"ms": e2e_ms, "h2d": rows_up * W * 32 + 31200, "d2h": (y1 - y0) * W * 16}
+        e2e = {"ms": e2e_ms, "h2d": strips.h2d_bytes(rank, world, W, Hh), "d2h": own_rows * W * 16}
 
     ms_per_step = total_ms / args.steps
     vals = torch.tensor([ms_per_step, float(st.rays), e2e["ms"] if e2e else 0.0, kavg["light_ms"], kavg["taa_ms"],
@@ -241,6 +243,11 @@ def run_ours(args):
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
     else:
         mx, sm = vals, vals
+    per_rank_light = [kavg["light_ms"]]
+    if world > 1:
+        lt = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(lt, torch.tensor([kavg["light_ms"]], dtype=torch.float64, device="cuda"))
+        per_rank_light = [float(t.item()) for t in lt]
     mx, sm = mx.cpu().numpy(), sm.cpu().numpy()
     ms_per_step = float(mx[0])
     rays_frame = float(sm[1])
@@ -254,9 +261,11 @@ def run_ours(args):
         l2_gbs = rt.probe_read_bandwidth(32 << 20, 200)
         hbm_probe = rt.probe_read_bandwidth(4 << 30, 4)
         light_ms, taa_ms = float(mx[3]), float(mx[4])
-        own_px = W * (y1 - y0)
-        trav_bytes = 80.0 * float(st.nodes_visited) + 48.0 * float(st.triangles_tested) + 64.0 * float(st.instances_entered)
-        shade_rows = (y1 - y0) + (2 if world > 1 else 0)
+        # per-GPU figures: the slowest rank's kernel time against the mean rank's work
+        own_px = W * own_rows
+        nodes, tris, insts, rays_r = float(sm[7]) / world, float(sm[8]) / world, float(sm[9]) / world, rays_frame / world
+        trav_bytes = 80.0 * nodes + 48.0 * tris + 64.0 * insts
+        shade_rows = len(strips.shaded_rows(rank, world, Hh))
         light_bytes = trav_bytes + 48.0 * W * shade_rows
         out = {
             "metric": METRIC, "value": rays_frame / ms_per_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
@@ -265,10 +274,12 @@ def run_ours(args):
             "config": {"workload": "%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px%s" % (
                 args.config, W, Hh, len(app.instances()), app.light_count(), cfg["light_samples"], cfg["ao_samples"],
                 (", TLAS %s per frame" % animate) if animate else ""),
-                "parallelism": "image strips x%d + ncclAllGather" % world if world > 1 else "1 GPU",
+                "parallelism": ("round-robin bands of %d rows x%d + ncclAllGather" % (strips.band_rows(Hh, world), world))
+                if world > 1 else "1 GPU",
                 "rays_per_frame": rays_frame, "lit_pixels": float(sm[10]),
                 "l2_policy": "inputs larger than L2 (G-buffer + 3 light buffers = %.0f MB > 126 MB)" % (W * Hh * 80 / 1e6)},
-            "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6])},
+            "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6]),
+                           "light_per_rank": [round(v, 4) for v in per_rank_light]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             # the dominant kernel against the measured HBM copy peak (the contract's roofline); its BVH working set is
@@ -281,11 +292,11 @@ def run_ours(args):
                          "peak_source": hbm_src,
                          "algorithmic_bytes": "48 B/px streamed + 80 B/node + 48 B/triangle + 64 B/instance fetched per ray",
                          "stream_bytes": 48.0 * W * shade_rows, "traversal_bytes": trav_bytes,
-                         "bytes_per_ray": trav_bytes / max(float(st.rays), 1.0),
-                         "nodes_per_ray": float(st.nodes_visited) / max(float(st.rays), 1.0),
-                         "tris_per_ray": float(st.triangles_tested) / max(float(st.rays), 1.0),
-                         "instances_per_ray": float(st.instances_entered) / max(float(st.rays), 1.0),
-                         "grays_per_s": float(st.rays) / (light_ms * 1e6)},
+                         "bytes_per_ray": trav_bytes / max(rays_r, 1.0),
+                         "nodes_per_ray": nodes / max(rays_r, 1.0),
+                         "tris_per_ray": tris / max(rays_r, 1.0),
+                         "instances_per_ray": insts / max(rays_r, 1.0),
+                         "grays_per_s_per_gpu": rays_r / (light_ms * 1e6)},
             "roofline_l2": {"kernel": "k_light_pass", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
                             "peak": l2_gbs, "unit": "GB/s", "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None,
                             "peak_source": "luzrt_probe_read_bandwidth, 32 MiB resident buffer, measured in this run"},
@@ -404,6 +415,10 @@ def run_reference(args):
 
 
 def main():
+    # stdout carries exactly one JSON line: libraries that print banners to fd 1 (NCCL's version line) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -204,13 +204,20 @@ LUZRT_API int luzrt_swap_light_history(luzrt_ctx* ctx);
 LUZRT_API int luzrt_read(luzrt_ctx* ctx, int which, void* dst, size_t bytes);
 /* Same for image selectors, restricted to rows [y0, y1): dst receives (y1-y0) packed rows. */
 LUZRT_API int luzrt_read_rows(luzrt_ctx* ctx, int which, uint32_t y0, uint32_t y1, void* dst, size_t bytes);
-/* The rows this ctx owns: [*y0, *y1) (the whole image when world == 1). */
-LUZRT_API int luzrt_owned_rows(luzrt_ctx* ctx, uint32_t* y0, uint32_t* y1);
+/* The rows this ctx owns.  A frame shared by `world` GPUs is cut into bands of *band_rows rows that are dealt
+ * round-robin (band b belongs to rank b % world, which balances sky against geometry): this ctx owns rows
+ * [*first_row + k * *pitch, + *band_rows) for k = 0 .. *n_bands-1.  world == 1: one band, the whole image. */
+LUZRT_API int luzrt_owned_bands(luzrt_ctx* ctx, uint32_t* first_row, uint32_t* band_rows, uint32_t* pitch,
+                                uint32_t* n_bands);
+/* Blocking read-back of the rows this ctx owns, packed in band order (height / world rows). */
+LUZRT_API int luzrt_read_owned(luzrt_ctx* ctx, int which, void* dst, size_t bytes);
 /* Measurement aid ("L2 peak must be measured by the builder"): streams a
  * `bytes`-sized device buffer `iters` times with every SM and returns the achieved read GB/s.
  * A buffer well below the 126 MB L2 measures L2 bandwidth, one far above it measures HBM. */
 LUZRT_API int luzrt_probe_read_bandwidth(luzrt_ctx* ctx, size_t bytes, int iters, double* out_gbs);
-/* Device pointer of an image selector (for hosts that keep working on the GPU). */
+/* Device pointer of an image selector (for hosts that keep working on the GPU).  With world > 1 the two
+ * light images are stored band-permuted (each rank's rows contiguous, rank-major): row y lives at
+ * (b % world) * (H / world) + (b / world) * band_rows + y % band_rows with b = y / band_rows. */
 LUZRT_API int luzrt_device_ptr(luzrt_ctx* ctx, int which, void** out_ptr, size_t* out_bytes);
 LUZRT_API int luzrt_sync(luzrt_ctx* ctx);
 /* The ctx's cudaStream_t as an integer, so a host can time with events on the same stream. */

@@ -70,7 +70,10 @@ struct luzrt_ctx {
     uint64_t launches = 0;
     uint32_t debug = 0;
 
-    uint32_t w = 0, h = 0, y0 = 0, y1 = 0;
+    uint32_t w = 0, h = 0;
+    uint32_t band_rows = 0, n_bands = 0, rows_per_rank = 0; // image partition
+    float4* unperm = nullptr;                               // staging for reads of banded images (world > 1)
+    size_t unperm_cap = 0;
     uchar4 *albedo = nullptr, *material = nullptr, *emission = nullptr, *compose = nullptr;
     float4 *normal = nullptr, *lightA = nullptr, *lightB = nullptr, *lightHist = nullptr;
     float* depth = nullptr;
@@ -122,6 +125,11 @@ struct luzrt_ctx {
     bool ev_valid[EV_COUNT]{};
 
     ncclComm_t comm = nullptr;
+    // the frame gather runs on its own stream so that it overlaps the next frame's light pass; whoever touches
+    // the buffer being gathered waits for ev_gathered first (wait_gather)
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_resolved = nullptr, ev_gathered = nullptr;
+    const void* gather_buf = nullptr; // image with a gather in flight (nullptr: none)
 };
 
 namespace {
@@ -178,6 +186,14 @@ int grow(luzrt_ctx* c, T*& p, size_t& cap, size_t need) {
     return LUZRT_OK;
 }
 
+// makes the ctx stream wait for the in-flight gather if it targets one of the given buffers (nullptr = any)
+cudaError_t wait_gather(luzrt_ctx* c, const void* a = nullptr, const void* b = nullptr, const void* d = nullptr) {
+    if (!c->gather_buf) return cudaSuccess;
+    if (a && c->gather_buf != a && c->gather_buf != b && c->gather_buf != d) return cudaSuccess;
+    c->gather_buf = nullptr;
+    return cudaStreamWaitEvent(c->stream, c->ev_gathered, 0);
+}
+
 void ev_begin(luzrt_ctx* c, int which) { cudaEventRecord(c->ev[which][0], c->stream); }
 void ev_end(luzrt_ctx* c, int which) {
     cudaEventRecord(c->ev[which][1], c->stream);
@@ -201,6 +217,30 @@ void free_blas(Blas& b) {
     if (b.indices) cudaFree(b.indices);
     b = Blas();
 }
+
+// rows this rank resolves / shades (own bands; own bands + one halo row each side for TAA's 3x3 taps)
+BandSet own_bands(const luzrt_ctx* c) {
+    if (c->world == 1) return BandSet{0, c->h, c->h, 1};
+    return BandSet{(int)((uint32_t)c->rank * c->band_rows), (uint32_t)c->world * c->band_rows, c->band_rows, c->n_bands};
+}
+BandSet shade_bands(const luzrt_ctx* c) {
+    if (c->world == 1) return BandSet{0, c->h, c->h, 1};
+    return BandSet{(int)((uint32_t)c->rank * c->band_rows) - 1, (uint32_t)c->world * c->band_rows, c->band_rows + 2,
+                   c->n_bands};
+}
+// smallest band height >= 48 rows that divides a rank's share (more bands = better balance, more halo rows)
+uint32_t choose_band_rows(uint32_t rows_per_rank) {
+    static const uint32_t min_rows = [] { // LUZRT_BAND_ROWS_MIN: tuning knob (luz_b200/strips.py reads it too)
+        const char* e = getenv("LUZRT_BAND_ROWS_MIN");
+        const int v = e ? atoi(e) : 48;
+        return (uint32_t)(v >= 2 ? v : 2);
+    }();
+    uint32_t best = rows_per_rank;
+    for (uint32_t k = 1; k <= rows_per_rank; k++)
+        if (rows_per_rank % k == 0 && rows_per_rank / k >= min_rows) best = rows_per_rank / k;
+    return best;
+}
+bool is_light_image(int which) { return which == LUZRT_IMG_LIGHT || which == LUZRT_IMG_HISTORY; }
 
 void* image_ptr(luzrt_ctx* c, int which, size_t* bytes) {
     const size_t px = (size_t)c->w * c->h;
@@ -261,12 +301,17 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (!c) return;
     DeviceGuard g(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->ev_resolved) cudaEventDestroy(c->ev_resolved);
+    if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     free_images(c);
     for (auto& b : c->blas) free_blas(b);
     free_wide_bvh(c->tlas);
     for (auto& t : c->textures)
         if (t.data) cudaFree(t.data);
+    if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
                     c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit};
@@ -301,6 +346,9 @@ int luzrt_comm_init(luzrt_ctx* c, const void* id128) {
     memcpy(&id, id128, 128);
     ncclResult_t r = g_nccl.CommInitRank(&c->comm, c->world, id, c->rank);
     if (r != ncclSuccess) return fail(c, LUZRT_E_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    CU(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
     return LUZRT_OK;
 }
 
@@ -308,8 +356,12 @@ int luzrt_resize(luzrt_ctx* c, uint32_t width, uint32_t height) {
     if (!c) return LUZRT_E_INVALID;
     REQUIRE(c, width > 0 && height > 0 && width <= 65536 && height <= 65536, "bad image size");
     REQUIRE(c, height % (uint32_t)c->world == 0, "height must be divisible by the number of ranks");
+    REQUIRE(c, c->world == 1 || height / (uint32_t)c->world >= 2, "a rank needs at least two rows");
+    REQUIRE(c, (c->world & (c->world - 1)) == 0, "the number of ranks must be a power of two");
     DeviceGuard g(c->device);
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->comm_stream) CU(c, cudaStreamSynchronize(c->comm_stream));
+    c->gather_buf = nullptr;
     free_images(c);
     const size_t px = (size_t)width * height;
     CU(c, cudaMalloc(&c->albedo, px * 4));
@@ -337,11 +389,17 @@ int luzrt_resize(luzrt_ctx* c, uint32_t width, uint32_t height) {
     }
     c->w = width;
     c->h = height;
-    c->y0 = (uint32_t)c->rank * (height / (uint32_t)c->world);
-    c->y1 = c->y0 + height / (uint32_t)c->world;
+    c->rows_per_rank = height / (uint32_t)c->world;
+    c->band_rows = c->world == 1 ? height : choose_band_rows(c->rows_per_rank);
+    c->n_bands = c->rows_per_rank / c->band_rows;
     c->history_valid = false;
     c->fc.width = width;
     c->fc.height = height;
+    c->fc.band_rows = c->band_rows;
+    c->fc.band_magic = (uint32_t)((0x100000000ull + c->band_rows - 1) / c->band_rows);
+    c->fc.world_shift = 0;
+    while ((1 << c->fc.world_shift) < c->world) c->fc.world_shift++;
+    c->fc.rows_per_rank = c->rows_per_rank;
     return LUZRT_OK;
 }
 
@@ -615,26 +673,43 @@ int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, cons
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
     DeviceGuard g(c->device);
     const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    // row ranges this ctx shades: everything on one GPU, else own strip + one wrapped row on each side
-    uint32_t seg[3][2];
-    int nseg = 0;
-    if (c->world == 1 || c->y1 - c->y0 + 2 >= c->h) {
-        seg[nseg][0] = 0, seg[nseg++][1] = c->h;
-    } else {
-        const uint32_t lo = c->y0 == 0 ? 0 : c->y0 - 1, hi = c->y1 == c->h ? c->h : c->y1 + 1;
-        seg[nseg][0] = lo, seg[nseg++][1] = hi;
-        if (c->y0 == 0) seg[nseg][0] = c->h - 1, seg[nseg++][1] = c->h;
-        if (c->y1 == c->h) seg[nseg][0] = 0, seg[nseg++][1] = 1;
+    // row ranges this ctx shades: everything on one GPU, else each own band + one wrapped row on each side
+    std::vector<std::pair<uint32_t, uint32_t>> seg;
+    const BandSet sb = shade_bands(c);
+    for (uint32_t k = 0; k < sb.n_bands; k++) {
+        const int lo = sb.first + (int)(k * sb.pitch), hi = lo + (int)sb.rows;
+        if (lo < 0) seg.emplace_back(c->h - 1, c->h);
+        if (hi > (int)c->h) seg.emplace_back(0, 1);
+        seg.emplace_back((uint32_t)std::max(lo, 0), (uint32_t)std::min(hi, (int)c->h));
     }
     struct Plane { void* dst; const void* src; size_t bpp; } planes[5] = {
         {c->albedo, albedo, 4}, {c->normal, normal, 16}, {c->material, material, 4},
         {c->emission, emission, 4}, {c->depth, depth, 4}};
-    for (int s = 0; s < nseg; s++)
-        for (const Plane& p : planes) {
-            if (!p.src) continue;
-            const size_t off = (size_t)seg[s][0] * c->w * p.bpp, n = (size_t)(seg[s][1] - seg[s][0]) * c->w * p.bpp;
+    for (const Plane& p : planes) {
+        if (!p.src) continue;
+        const size_t row = (size_t)c->w * p.bpp;
+        // bands that lie fully inside the image repeat at a fixed pitch: one strided copy covers them all
+        size_t first_regular = seg.size(), n_regular = 0;
+        for (size_t s2 = 0; s2 < seg.size(); s2++) {
+            const bool regular = seg[s2].second - seg[s2].first == sb.rows;
+            if (regular && n_regular == 0) first_regular = s2;
+            if (regular && s2 == first_regular + n_regular &&
+                (n_regular == 0 || seg[s2].first == seg[first_regular].first + n_regular * sb.pitch))
+                n_regular++;
+        }
+        for (size_t s2 = 0; s2 < seg.size(); s2++) {
+            if (n_regular > 1 && s2 >= first_regular && s2 < first_regular + n_regular) {
+                if (s2 == first_regular) {
+                    const size_t off = (size_t)seg[s2].first * row;
+                    CU(c, cudaMemcpy2DAsync((char*)p.dst + off, (size_t)sb.pitch * row, (const char*)p.src + off,
+                                            (size_t)sb.pitch * row, (size_t)sb.rows * row, n_regular, kind, c->stream));
+                }
+                continue;
+            }
+            const size_t off = (size_t)seg[s2].first * row, n = (size_t)(seg[s2].second - seg[s2].first) * row;
             CU(c, cudaMemcpyAsync((char*)p.dst + off, (const char*)p.src + off, n, kind, c->stream));
         }
+    }
     return LUZRT_OK;
 }
 
@@ -697,13 +772,7 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     a.material = c->material;
     a.emission = c->emission;
     a.depth = c->depth;
-    if (c->world == 1) {
-        a.row_start = 0;
-        a.row_count = c->h;
-    } else {
-        a.row_start = (int)c->y0 - 1;
-        a.row_count = (c->y1 - c->y0) + 2;
-    }
+    a.rows = shade_bands(c);
     ev_begin(c, EV_GBUF);
     CU(c, launch_gbuffer_pass(c->stream, a));
     c->launches++;
@@ -749,13 +818,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.lights = c->d_lights;
     a.out = c->lightA;
     a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u};
-    if (c->world == 1) {
-        a.row_start = 0;
-        a.row_count = c->h;
-    } else { // own rows plus the row above and below (wrapping) that TAA's 3x3 taps read
-        a.row_start = (int)c->y0 - 1;
-        a.row_count = (c->y1 - c->y0) + 2;
-    }
+    a.rows = shade_bands(c); // own bands plus the row above and below each (wrapping) that TAA's 3x3 taps read
     a.shadow_mask = c->d_shadow_mask;
     a.shadow_words = (uint32_t)c->shadow_mask_words;
     a.ao_mask = c->d_ao_mask;
@@ -763,8 +826,8 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.stats = c->d_stats;
     a.lit_counters = c->d_lit;
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
-    a.count_row_end = c->world == 1 ? c->h : 1u + (c->y1 - c->y0);
-    a.rays_per_pixel = c->rays_per_lit_pixel;
+    a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
+    CU(c, wait_gather(c, a.out));
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
@@ -787,9 +850,9 @@ int luzrt_taa_pass(luzrt_ctx* c, int reconstruct) {
     a.history = c->history_valid ? c->lightHist : c->lightA;
     a.depth = c->depth;
     a.out = c->lightB;
-    a.row_start = c->y0;
-    a.row_count = c->y1 - c->y0;
+    a.rows = own_bands(c);
     a.reconstruct = reconstruct ? 1 : 0;
+    CU(c, wait_gather(c, a.light_in, a.history, a.out));
     ev_begin(c, EV_TAA);
     CU(c, launch_taa_pass(c->stream, a));
     c->launches++;
@@ -804,13 +867,19 @@ int luzrt_gather(luzrt_ctx* c) {
     if (!c->comm) return fail(c, LUZRT_E_STATE, "luzrt_comm_init has not been called");
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
     DeviceGuard g(c->device);
-    const size_t strip_floats = (size_t)(c->y1 - c->y0) * c->w * 4;
-    ev_begin(c, EV_GATHER);
-    // in place: this rank's strip already sits at its offset inside the full-frame buffer
+    const size_t strip_floats = (size_t)c->rows_per_rank * c->w * 4; // a rank's bands are contiguous in storage order
+    CU(c, wait_gather(c)); // one gather in flight at a time
+    CU(c, cudaEventRecord(c->ev_resolved, c->stream));
+    CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_resolved, 0));
+    cudaEventRecord(c->ev[EV_GATHER][0], c->comm_stream);
+    // in place: this rank's rows already sit at their offset inside the full-frame buffer
     ncclResult_t r = g_nccl.AllGather((const float*)c->lightA + (size_t)c->rank * strip_floats, c->lightA, strip_floats,
-                                      ncclFloat, c->comm, c->stream);
-    ev_end(c, EV_GATHER);
+                                      ncclFloat, c->comm, c->comm_stream);
+    cudaEventRecord(c->ev[EV_GATHER][1], c->comm_stream);
+    c->ev_valid[EV_GATHER] = true;
     if (r != ncclSuccess) return fail(c, LUZRT_E_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    CU(c, cudaEventRecord(c->ev_gathered, c->comm_stream));
+    c->gather_buf = c->lightA;
     return LUZRT_OK;
 }
 
@@ -820,7 +889,8 @@ int luzrt_compose_pass(luzrt_ctx* c, float exposure) {
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
     DeviceGuard g(c->device);
     ev_begin(c, EV_COMPOSE);
-    CU(c, launch_compose_pass(c->stream, c->lightA, c->compose, c->w, c->y0, c->y1 - c->y0));
+    // reads only this rank's own rows of lightA, which a gather in flight does not write
+    CU(c, launch_compose_pass(c->stream, c->fc, c->lightA, c->compose, own_bands(c)));
     c->launches++;
     ev_end(c, EV_COMPOSE);
     return LUZRT_OK;
@@ -837,6 +907,7 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
     if (!c) return LUZRT_E_INVALID;
     REQUIRE(c, dst, "dst is null");
     DeviceGuard g(c->device);
+    CU(c, wait_gather(c));
     CU(c, cudaStreamSynchronize(c->stream));
     if (which == LUZRT_STATS) {
         REQUIRE(c, bytes >= sizeof(luzrt_stats), "buffer too small for luzrt_stats");
@@ -871,6 +942,7 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
     void* src = image_ptr(c, which, &have);
     if (!src) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
     REQUIRE(c, bytes >= have, "destination buffer too small");
+    if (c->world > 1 && is_light_image(which)) return luzrt_read_rows(c, which, 0, c->h, dst, bytes);
     CU(c, cudaMemcpy(dst, src, have, cudaMemcpyDeviceToHost));
     return LUZRT_OK;
 }
@@ -880,20 +952,57 @@ int luzrt_read_rows(luzrt_ctx* c, int which, uint32_t y0, uint32_t y1, void* dst
     REQUIRE(c, dst, "dst is null");
     REQUIRE(c, y0 <= y1 && y1 <= c->h, "row range out of bounds");
     DeviceGuard g(c->device);
+    CU(c, wait_gather(c));
     size_t have = 0;
     void* src = image_ptr(c, which, &have);
     if (!src || !c->h) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
     const size_t row = have / c->h, need = row * (y1 - y0);
     REQUIRE(c, bytes >= need, "destination buffer too small");
-    CU(c, cudaMemcpyAsync(dst, (const char*)src + row * y0, need, cudaMemcpyDeviceToHost, c->stream));
+    if (c->world > 1 && is_light_image(which) && y1 > y0) {
+        // the light images of a partitioned frame are stored band-permuted: bring the rows to natural order first
+        int rc;
+        if ((rc = grow(c, c->unperm, c->unperm_cap, (size_t)c->w * (y1 - y0))) != LUZRT_OK) return rc;
+        CU(c, launch_unpermute_rows(c->stream, c->fc, (const float4*)src, c->unperm, y0, y1));
+        c->launches++;
+        CU(c, cudaMemcpyAsync(dst, c->unperm, need, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(c, cudaMemcpyAsync(dst, (const char*)src + row * y0, need, cudaMemcpyDeviceToHost, c->stream));
+    }
     CU(c, cudaStreamSynchronize(c->stream));
     return LUZRT_OK;
 }
 
-int luzrt_owned_rows(luzrt_ctx* c, uint32_t* y0, uint32_t* y1) {
-    if (!c || !y0 || !y1) return LUZRT_E_INVALID;
-    *y0 = c->y0;
-    *y1 = c->y1;
+int luzrt_owned_bands(luzrt_ctx* c, uint32_t* first_row, uint32_t* band_rows, uint32_t* pitch, uint32_t* n_bands) {
+    if (!c || !first_row || !band_rows || !pitch || !n_bands) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    const BandSet b = own_bands(c);
+    *first_row = (uint32_t)b.first;
+    *band_rows = b.rows;
+    *pitch = b.pitch;
+    *n_bands = b.n_bands;
+    return LUZRT_OK;
+}
+
+int luzrt_read_owned(luzrt_ctx* c, int which, void* dst, size_t bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, dst, "dst is null");
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    size_t have = 0;
+    void* src = image_ptr(c, which, &have);
+    if (!src) return fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
+    const size_t row = have / c->h, need = row * c->rows_per_rank;
+    REQUIRE(c, bytes >= need, "destination buffer too small");
+    if (is_light_image(which) || c->world == 1) {
+        // banded storage keeps a rank's rows contiguous: one copy
+        CU(c, cudaMemcpyAsync(dst, (const char*)src + row * c->rows_per_rank * (size_t)c->rank, need, cudaMemcpyDeviceToHost,
+                              c->stream));
+    } else {
+        const BandSet b = own_bands(c);
+        CU(c, cudaMemcpy2DAsync(dst, row * b.rows, (const char*)src + row * (size_t)b.first, row * b.pitch, row * b.rows,
+                                b.n_bands, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
     return LUZRT_OK;
 }
 
@@ -929,6 +1038,8 @@ int luzrt_probe_read_bandwidth(luzrt_ctx* c, size_t bytes, int iters, double* ou
 int luzrt_device_ptr(luzrt_ctx* c, int which, void** out_ptr, size_t* out_bytes) {
     if (!c) return LUZRT_E_INVALID;
     REQUIRE(c, out_ptr && out_bytes, "null output");
+    DeviceGuard g(c->device);
+    CU(c, wait_gather(c)); // work the host enqueues on the ctx stream after this call sees the gathered frame
     *out_ptr = image_ptr(c, which, out_bytes);
     return *out_ptr ? LUZRT_OK : fail(c, LUZRT_E_INVALID, "selector %d has no data", which);
 }
@@ -936,6 +1047,7 @@ int luzrt_device_ptr(luzrt_ctx* c, int which, void** out_ptr, size_t* out_bytes)
 int luzrt_sync(luzrt_ctx* c) {
     if (!c) return LUZRT_E_INVALID;
     DeviceGuard g(c->device);
+    CU(c, wait_gather(c));
     CU(c, cudaStreamSynchronize(c->stream));
     return LUZRT_OK;
 }

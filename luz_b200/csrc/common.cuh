@@ -86,6 +86,23 @@ struct FrameConst { // what the kernels need from SceneBlock, passed by value (k
     int frame_mod; // frame % 128
     uint32_t width, height;
     uint32_t bn_w, bn_h;
+    // Image partition over the GPUs of a box: the frame is cut into bands of band_rows
+    // rows, band b belongs to rank b % world.  The RGBA32F light images are stored with every rank's rows
+    // contiguous (rank-major, then band, then row) so that one in-place all-gather assembles them; the
+    // G-buffer keeps the natural row order.  world == 1: band_rows == height and storage_row is the identity.
+    uint32_t band_rows;     // rows per band
+    uint32_t band_magic;    // ceil(2^32 / band_rows): y / band_rows == umulhi(y, band_magic) for y < 65536
+    uint32_t world_shift;   // log2(world)
+    uint32_t rows_per_rank; // height / world
+};
+
+// Rows [band_first + z * band_pitch, + rows) for z = 0 .. n_bands-1 (wrapping at the image border like the
+// REPEAT sampler): the row sets a rank shades (own bands + one halo row each side) or resolves (own bands).
+struct BandSet {
+    int first;          // first row of band 0 (may be -1: the halo row above row 0 wraps to height-1)
+    uint32_t pitch;     // rows between the starts of successive bands of this rank
+    uint32_t rows;      // rows per band in this set
+    uint32_t n_bands;
 };
 
 struct DeviceStats {
@@ -127,6 +144,18 @@ __device__ inline float4 mat_mul(const float* m, float4 v) {
     r.z = m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w;
     r.w = m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w;
     return r;
+}
+
+__device__ __forceinline__ uint32_t storage_row(const FrameConst& fc, uint32_t y) {
+    const uint32_t b = __umulhi(y, fc.band_magic);
+    return (b & ((1u << fc.world_shift) - 1u)) * fc.rows_per_rank + (b >> fc.world_shift) * fc.band_rows +
+           (y - b * fc.band_rows);
+}
+__device__ __forceinline__ uint32_t band_row(const FrameConst& fc, const BandSet& bs, uint32_t z, uint32_t r) {
+    int y = bs.first + (int)(z * bs.pitch + r);
+    if (y < 0) y += (int)fc.height;
+    if (y >= (int)fc.height) y -= (int)fc.height;
+    return (uint32_t)y;
 }
 
 // utils.glsl:1-7

@@ -55,10 +55,8 @@ __global__ void __launch_bounds__(128) k_gbuffer(const GbufferArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t r = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
-    if (x >= fc.width || r >= a.row_count) return;
-    int yy = (a.row_start + (int)r) % (int)fc.height;
-    if (yy < 0) yy += (int)fc.height;
-    const uint32_t y = (uint32_t)yy;
+    if (x >= fc.width || r >= a.rows.rows) return;
+    const uint32_t y = band_row(fc, a.rows, blockIdx.z, r);
     const size_t pix = (size_t)y * fc.width + x;
 
     const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
@@ -172,8 +170,8 @@ __global__ void __launch_bounds__(128) k_gbuffer(const GbufferArgs a) {
 } // namespace
 
 cudaError_t launch_gbuffer_pass(cudaStream_t stream, const GbufferArgs& args) {
-    if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;
-    const dim3 grid((args.fc.width + 15) / 16, (args.row_count + 7) / 8);
+    if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
+    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands);
     k_gbuffer<<<grid, 128, 0, stream>>>(args);
     return cudaGetLastError();
 }

@@ -18,17 +18,15 @@ struct LightArgs {
     const LightRec* lights;
     float4* out;
     TraceScene scene;
-    int row_start;      // first image row to shade (may be negative / beyond H: rows wrap like the
-    uint32_t row_count; // REPEAT sampler TAA reads them with)
+    BandSet rows;       // rows to shade: own bands plus the halo rows TAA's 3x3 taps read
     uint32_t* shadow_mask;
     uint32_t shadow_words;
     uint32_t* ao_mask;
     uint32_t ao_words;
     DeviceStats* stats;
     unsigned long long* lit_counters; // 64 counters, 128 B apart
-    uint32_t count_row_begin, count_row_end; // rows (relative to row_start) whose lit pixels are counted
-    uint32_t node_repeat;                    // TRACE: keep visiting nodes while at least this many lanes can
-    uint32_t rays_per_pixel;                 // sum of numShadowSamples over the lights (ray-traced shadows) + aoNumSamples
+    uint32_t count_row_begin, count_row_end; // rows (relative to a band's first row) whose lit pixels are counted
+    uint32_t cand_offset;                    // byte offset of the AO candidate lists in dynamic shared memory
 };
 
 struct TaaArgs {
@@ -37,7 +35,7 @@ struct TaaArgs {
     const float4* history;
     const float* depth;
     float4* out;
-    uint32_t row_start, row_count;
+    BandSet rows; // own bands
     int reconstruct;
 };
 
@@ -56,14 +54,16 @@ struct GbufferArgs {
     uchar4* material;
     uchar4* emission;
     float* depth;
-    int row_start;
-    uint32_t row_count;
+    BandSet rows;
 };
 
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats);
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
-cudaError_t launch_compose_pass(cudaStream_t stream, const float4* light_in, uchar4* out_bgra, uint32_t width,
-                                uint32_t row_start, uint32_t row_count);
+cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,
+                                const BandSet& rows);
+// copies rows between the banded storage order of the light images and the natural row order
+cudaError_t launch_unpermute_rows(cudaStream_t stream, const FrameConst& fc, const float4* banded, float4* natural,
+                                  uint32_t y0, uint32_t y1);
 cudaError_t launch_gbuffer_pass(cudaStream_t stream, const GbufferArgs& args);
 // bandwidth probe: every SM streams `bytes` of `buf` `iters` times with 128-bit loads
 cudaError_t launch_probe_read(cudaStream_t stream, const void* buf, size_t bytes, int iters, float* sink);

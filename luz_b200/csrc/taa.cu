@@ -21,11 +21,12 @@ __device__ __forceinline__ int wrapi(int i, int n) {
 // REPEAT addressing for coordinates known to lie in [-n, 2n): no integer division
 __device__ __forceinline__ int wrap1(int i, int n) { return i < 0 ? i + n : (i >= n ? i - n : i); }
 
-struct Img {
+struct Img { // an RGBA32F light image in banded storage order (common.cuh: storage_row)
     const float4* p;
+    const FrameConst* fc;
     int w, h;
     __device__ __forceinline__ float4 texel(int x, int y) const { // x, y within one period of the image
-        return __ldg(p + (size_t)wrap1(y, h) * w + wrap1(x, w));
+        return __ldg(p + (size_t)storage_row(*fc, (uint32_t)wrap1(y, h)) * w + wrap1(x, w));
     }
 };
 
@@ -53,11 +54,11 @@ __global__ void __launch_bounds__(256) k_taa(const TaaArgs a) {
     const FrameConst& fc = a.fc;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ry = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= (int)fc.width || ry >= (int)a.row_count) return;
-    const int y = (int)a.row_start + ry;
+    if (x >= (int)fc.width || ry >= (int)a.rows.rows) return;
+    const int y = (int)band_row(fc, a.rows, blockIdx.z, (uint32_t)ry);
     const int W = (int)fc.width, H = (int)fc.height;
     const float sw = (float)W, sh = (float)H;
-    const Img light{a.light_in, W, H}, hist{a.history, W, H};
+    const Img light{a.light_in, &fc, W, H}, hist{a.history, &fc, W, H};
 
     const float su = ((float)x + 0.5f) / sw, sv = ((float)y + 0.5f) / sh; // get_uv
     // find_closest_3x3: first strict minimum in row-major order
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(256) k_taa(const TaaArgs a) {
     }
     if (a.reconstruct == 0 || any_nan4(sourceSample)) sourceSample = cmc;
 
-    float4* dst = a.out + (size_t)y * W + x;
+    float4* dst = a.out + (size_t)storage_row(fc, (uint32_t)y) * W + x;
     if (hu > 1.0f || hv > 1.0f || hu < 0.0f || hv < 0.0f) {
         *dst = sourceSample;
         return;
@@ -177,11 +178,12 @@ __device__ __forceinline__ unsigned char unorm8(float v) {
     return (unsigned char)(int)floorf(v * 255.0f + 0.5f);
 }
 
-__global__ void __launch_bounds__(256) k_compose(const float4* __restrict__ light_in, uchar4* __restrict__ out,
-                                                 size_t first, size_t count) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    const float4 c = __ldg(light_in + first + i);
+__global__ void __launch_bounds__(256) k_compose(const FrameConst fc, const float4* __restrict__ light_in,
+                                                 uchar4* __restrict__ out, const BandSet rows) {
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), r = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= fc.width || r >= rows.rows) return;
+    const uint32_t y = band_row(fc, rows, blockIdx.z, r);
+    const float4 c = __ldg(light_in + (size_t)storage_row(fc, y) * fc.width + x);
     const float a = 2.51f, b = 0.03f, cc = 2.43f, d = 0.59f, e = 0.14f;
     const float in[3] = {c.x, c.y, c.z};
     float o[3];
@@ -191,7 +193,14 @@ __global__ void __launch_bounds__(256) k_compose(const float4* __restrict__ ligh
         const float m = (x * (a * x + b)) / (x * (cc * x + d) + e);
         o[k] = powf(m, 1.0f / 2.2f);
     }
-    out[first + i] = make_uchar4(unorm8(o[2]), unorm8(o[1]), unorm8(o[0]), 255); // BGRA8
+    out[(size_t)y * fc.width + x] = make_uchar4(unorm8(o[2]), unorm8(o[1]), unorm8(o[0]), 255); // BGRA8, natural rows
+}
+
+__global__ void __launch_bounds__(256) k_unpermute(const FrameConst fc, const float4* __restrict__ banded,
+                                                   float4* __restrict__ natural, uint32_t y0, uint32_t y1) {
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= fc.width || y >= y1) return;
+    natural[(size_t)(y - y0) * fc.width + x] = __ldg(banded + (size_t)storage_row(fc, y) * fc.width + x);
 }
 
 __global__ void __launch_bounds__(512) k_probe_read(const uint4* __restrict__ buf, size_t n16, int iters,
@@ -218,18 +227,25 @@ cudaError_t launch_probe_read(cudaStream_t stream, const void* buf, size_t bytes
 }
 
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args) {
-    if (args.row_count == 0 || args.fc.width == 0) return cudaSuccess;
-    const dim3 grid((args.fc.width + 31) / 32, (args.row_count + 7) / 8);
+    if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
+    const dim3 grid((args.fc.width + 31) / 32, (args.rows.rows + 7) / 8, args.rows.n_bands);
     k_taa<<<grid, 256, 0, stream>>>(args);
     return cudaGetLastError();
 }
 
-cudaError_t launch_compose_pass(cudaStream_t stream, const float4* light_in, uchar4* out_bgra, uint32_t width,
-                                uint32_t row_start, uint32_t row_count) {
-    const size_t count = (size_t)width * row_count;
-    if (!count) return cudaSuccess;
-    k_compose<<<(unsigned)((count + 255) / 256), 256, 0, stream>>>(light_in, out_bgra, (size_t)width * row_start,
-                                                                   count);
+cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,
+                                const BandSet& rows) {
+    if (rows.rows == 0 || rows.n_bands == 0 || fc.width == 0) return cudaSuccess;
+    const dim3 grid((fc.width + 31) / 32, (rows.rows + 7) / 8, rows.n_bands);
+    k_compose<<<grid, 256, 0, stream>>>(fc, light_in, out_bgra, rows);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpermute_rows(cudaStream_t stream, const FrameConst& fc, const float4* banded, float4* natural,
+                                  uint32_t y0, uint32_t y1) {
+    if (y1 <= y0 || fc.width == 0) return cudaSuccess;
+    const dim3 grid((fc.width + 31) / 32, (y1 - y0 + 7) / 8);
+    k_unpermute<<<grid, 256, 0, stream>>>(fc, banded, natural, y0, y1);
     return cudaGetLastError();
 }
 

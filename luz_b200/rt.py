@@ -22,7 +22,7 @@ EXPORTS = [
     "luzrt_blas_destroy", "luzrt_blas_dump", "luzrt_tlas_dump", "luzrt_tlas_build", "luzrt_set_scene",
     "luzrt_set_gbuffer", "luzrt_gbuffer_pass", "luzrt_set_debug", "luzrt_light_pass", "luzrt_taa_pass",
     "luzrt_gather", "luzrt_compose_pass", "luzrt_swap_light_history", "luzrt_read", "luzrt_device_ptr",
-    "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_rows",
+    "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_bands", "luzrt_read_owned",
     "luzrt_probe_read_bandwidth",
 ]
 
@@ -74,7 +74,8 @@ def load_library():
         "luzrt_stream": (i32, [vp, C.POINTER(u64)]),
         "luzrt_launch_count": (u64, [vp]),
         "luzrt_read_rows": (i32, [vp, i32, u32, u32, vp, C.c_size_t]),
-        "luzrt_owned_rows": (i32, [vp, C.POINTER(u32), C.POINTER(u32)]),
+        "luzrt_owned_bands": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
+        "luzrt_read_owned": (i32, [vp, i32, vp, C.c_size_t]),
         "luzrt_probe_read_bandwidth": (i32, [vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
@@ -232,10 +233,15 @@ class LuzRT:
     def launch_count(self):
         return int(self.lib.luzrt_launch_count(self.h))
 
-    def owned_rows(self):
-        a, b = C.c_uint32(), C.c_uint32()
-        self._ck(self.lib.luzrt_owned_rows(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
+    def owned_bands(self):
+        """(first_row, band_rows, pitch, n_bands): this ctx owns rows [first + k*pitch, + band_rows), k < n_bands."""
+        v = [C.c_uint32() for _ in range(4)]
+        self._ck(self.lib.luzrt_owned_bands(self.h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def read_owned(self, which, out):
+        self._ck(self.lib.luzrt_read_owned(self.h, which, _ptr(out), out.nbytes))
+        return out
 
     def read_rows(self, which, y0, y1, out):
         self._ck(self.lib.luzrt_read_rows(self.h, which, y0, y1, _ptr(out), out.nbytes))
