@@ -130,6 +130,7 @@ struct luzrt_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_resolved = nullptr, ev_gathered = nullptr;
     const void* gather_buf = nullptr; // image with a gather in flight (nullptr: none)
+    uint32_t min_node_lanes = 33; // > 32: one node visit per pass of the traversal loop (fastest on C2-C4; LUZRT_MIN_NODE_LANES)
 };
 
 namespace {
@@ -292,6 +293,7 @@ int luzrt_create(int device_id, int rank, int world, luzrt_ctx** out) {
     }
     cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream);
     cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream);
+    if (const char* e = getenv("LUZRT_MIN_NODE_LANES")) c->min_node_lanes = (uint32_t)atoi(e);
     c->blas.emplace_back(); // handle 0 is invalid
     *out = c;
     return LUZRT_OK;
@@ -759,7 +761,7 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     }
     GbufferArgs a{};
     a.fc = c->fc;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u, c->min_node_lanes};
     a.inst_meta = c->d_meta;
     a.blas_attr = c->d_blas_attr;
     a.models = c->d_models;
@@ -817,7 +819,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.blue_noise = c->blue_noise;
     a.lights = c->d_lights;
     a.out = c->lightA;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u, c->min_node_lanes};
     a.rows = shade_bands(c); // own bands plus the row above and below each (wrapping) that TAA's 3x3 taps read
     a.shadow_mask = c->d_shadow_mask;
     a.shadow_words = (uint32_t)c->shadow_mask_words;

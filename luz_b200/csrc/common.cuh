@@ -57,6 +57,7 @@ struct TraceScene {
     const InstanceRec* instances;
     const float4* inst_boxes; // world boxes of the instances, TLAS leaf order: [2i] = lo.xyz, [2i+1] = hi.xyz
     uint32_t one_bits; // 0x3F800000, deliberately a run-time value (see traverse.cuh)
+    uint32_t min_node_lanes; // the node loop of trace_ray yields once fewer lanes than this remain in it
 };
 
 // compact light record staged in shared memory (first 64 bytes of a LightBlock)

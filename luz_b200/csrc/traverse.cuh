@@ -309,6 +309,9 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             const uint32_t node_imask = n0.w >> 24;
             ngroup = make_uint2(n1.x, ((slots & node_imask) << 24) | node_imask);
             tgroup = make_uint2(n1.y, leaf_bits(slots & ~node_imask, n1.z, n1.w));
+            // when only a few lanes are still descending, yield so that the lanes waiting at the end of this loop
+            // (they hold primitives or need a pop) get served and everybody re-enters the node test together
+            if (__popc(__activemask()) < (int)sc.min_node_lanes) break;
         }
 
         while (tgroup.y != 0u) {
