@@ -171,6 +171,14 @@ LUZRT_API int luzrt_set_gbuffer(luzrt_ctx* ctx, const void* albedo_rgba8, const 
                                 const void* material_rgba8, const void* emission_rgba8,
                                 const void* depth_f32, int src_is_device);
 
+/* Pipelined host path (the reference keeps 3 frames in flight, VulkanWrapper.cpp:178): the five planes of the
+ * NEXT frame are copied from page-locked host memory into a second G-buffer set on a copy stream while the
+ * current frame is still being shaded; luzrt_flip_gbuffer then makes that set current (the ctx stream waits
+ * for the copy).  The host buffers must stay valid until the flip. */
+LUZRT_API int luzrt_prefetch_gbuffer(luzrt_ctx* ctx, const void* albedo_rgba8, const void* normal_rgba32f,
+                                     const void* material_rgba8, const void* emission_rgba8, const void* depth_f32);
+LUZRT_API int luzrt_flip_gbuffer(luzrt_ctx* ctx);
+
 /* produces the same five attachments on the device by primary
  * visibility through the TLAS (closest hit), restating opaque.vert:21-31 / opaque.frag:21-59;
  * models[i] is addressed by luzrt_instance.custom_index (GPUScene.cpp:188-191). */
@@ -211,6 +219,10 @@ LUZRT_API int luzrt_owned_bands(luzrt_ctx* ctx, uint32_t* first_row, uint32_t* b
                                 uint32_t* n_bands);
 /* Blocking read-back of the rows this ctx owns, packed in band order (height / world rows). */
 LUZRT_API int luzrt_read_owned(luzrt_ctx* ctx, int which, void* dst, size_t bytes);
+/* Non-blocking variant for LUZRT_IMG_LIGHT / LUZRT_IMG_HISTORY: the copy into page-locked dst runs on a copy
+ * stream after the work enqueued so far; luzrt_read_wait blocks until it has landed.  One read in flight. */
+LUZRT_API int luzrt_read_owned_async(luzrt_ctx* ctx, int which, void* dst, size_t bytes);
+LUZRT_API int luzrt_read_wait(luzrt_ctx* ctx);
 /* Measurement aid ("L2 peak must be measured by the builder"): streams a
  * `bytes`-sized device buffer `iters` times with every SM and returns the achieved read GB/s.
  * A buffer well below the 126 MB L2 measures L2 bandwidth, one far above it measures HBM. */

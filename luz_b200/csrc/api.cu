@@ -77,6 +77,13 @@ struct luzrt_ctx {
     uchar4 *albedo = nullptr, *material = nullptr, *emission = nullptr, *compose = nullptr;
     float4 *normal = nullptr, *lightA = nullptr, *lightB = nullptr, *lightHist = nullptr;
     float* depth = nullptr;
+    // back G-buffer set + streams of the pipelined host path (luzrt_prefetch_gbuffer / luzrt_read_owned_async)
+    uchar4 *albedo_b = nullptr, *material_b = nullptr, *emission_b = nullptr;
+    float4* normal_b = nullptr;
+    float* depth_b = nullptr;
+    cudaStream_t upload_stream = nullptr, download_stream = nullptr;
+    cudaEvent_t ev_flip = nullptr, ev_uploaded = nullptr, ev_result = nullptr, ev_downloaded = nullptr;
+    bool upload_pending = false, download_pending = false;
     bool history_valid = false;
 
     uchar4* blue_noise = nullptr;
@@ -203,9 +210,13 @@ void ev_end(luzrt_ctx* c, int which) {
 
 void free_images(luzrt_ctx* c) {
     void* ptrs[] = {c->albedo, c->material, c->emission, c->compose, c->normal, c->lightA, c->lightB, c->lightHist,
-                    c->depth};
+                    c->depth, c->albedo_b, c->material_b, c->emission_b, c->normal_b, c->depth_b};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    c->albedo_b = c->material_b = c->emission_b = nullptr;
+    c->normal_b = nullptr;
+    c->depth_b = nullptr;
+    c->upload_pending = c->download_pending = false;
     c->albedo = c->material = c->emission = c->compose = nullptr;
     c->normal = c->lightA = c->lightB = c->lightHist = nullptr;
     c->depth = nullptr;
@@ -305,6 +316,13 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (cudaStream_t st : {c->upload_stream, c->download_stream})
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    for (cudaEvent_t e : {c->ev_flip, c->ev_uploaded, c->ev_result, c->ev_downloaded})
+        if (e) cudaEventDestroy(e);
     if (c->ev_resolved) cudaEventDestroy(c->ev_resolved);
     if (c->ev_gathered) cudaEventDestroy(c->ev_gathered);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -363,6 +381,8 @@ int luzrt_resize(luzrt_ctx* c, uint32_t width, uint32_t height) {
     DeviceGuard g(c->device);
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->comm_stream) CU(c, cudaStreamSynchronize(c->comm_stream));
+    if (c->upload_stream) CU(c, cudaStreamSynchronize(c->upload_stream));
+    if (c->download_stream) CU(c, cudaStreamSynchronize(c->download_stream));
     c->gather_buf = nullptr;
     free_images(c);
     const size_t px = (size_t)width * height;
@@ -669,13 +689,13 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
     return LUZRT_OK;
 }
 
-int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, const void* material,
-                      const void* emission, const void* depth, int src_is_device) {
-    if (!c) return LUZRT_E_INVALID;
-    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
-    DeviceGuard g(c->device);
-    const cudaMemcpyKind kind = src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    // row ranges this ctx shades: everything on one GPU, else each own band + one wrapped row on each side
+namespace {
+struct GbufPlanes {
+    void* p[5]; // albedo, normal, material, emission, depth
+};
+// Copies the rows this ctx shades (everything on one GPU, else each own band + one wrapped row on each side) of
+// the given full-frame planes; null sources are skipped.
+int copy_gbuffer(luzrt_ctx* c, const GbufPlanes& dst, const void* const src[5], cudaMemcpyKind kind, cudaStream_t stream) {
     std::vector<std::pair<uint32_t, uint32_t>> seg;
     const BandSet sb = shade_bands(c);
     for (uint32_t k = 0; k < sb.n_bands; k++) {
@@ -684,12 +704,10 @@ int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, cons
         if (hi > (int)c->h) seg.emplace_back(0, 1);
         seg.emplace_back((uint32_t)std::max(lo, 0), (uint32_t)std::min(hi, (int)c->h));
     }
-    struct Plane { void* dst; const void* src; size_t bpp; } planes[5] = {
-        {c->albedo, albedo, 4}, {c->normal, normal, 16}, {c->material, material, 4},
-        {c->emission, emission, 4}, {c->depth, depth, 4}};
-    for (const Plane& p : planes) {
-        if (!p.src) continue;
-        const size_t row = (size_t)c->w * p.bpp;
+    static const size_t bpp[5] = {4, 16, 4, 4, 4};
+    for (int pl = 0; pl < 5; pl++) {
+        if (!src[pl]) continue;
+        const size_t row = (size_t)c->w * bpp[pl];
         // bands that lie fully inside the image repeat at a fixed pitch: one strided copy covers them all
         size_t first_regular = seg.size(), n_regular = 0;
         for (size_t s2 = 0; s2 < seg.size(); s2++) {
@@ -703,15 +721,106 @@ int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, cons
             if (n_regular > 1 && s2 >= first_regular && s2 < first_regular + n_regular) {
                 if (s2 == first_regular) {
                     const size_t off = (size_t)seg[s2].first * row;
-                    CU(c, cudaMemcpy2DAsync((char*)p.dst + off, (size_t)sb.pitch * row, (const char*)p.src + off,
-                                            (size_t)sb.pitch * row, (size_t)sb.rows * row, n_regular, kind, c->stream));
+                    CU(c, cudaMemcpy2DAsync((char*)dst.p[pl] + off, (size_t)sb.pitch * row, (const char*)src[pl] + off,
+                                            (size_t)sb.pitch * row, (size_t)sb.rows * row, n_regular, kind, stream));
                 }
                 continue;
             }
             const size_t off = (size_t)seg[s2].first * row, n = (size_t)(seg[s2].second - seg[s2].first) * row;
-            CU(c, cudaMemcpyAsync((char*)p.dst + off, (const char*)p.src + off, n, kind, c->stream));
+            CU(c, cudaMemcpyAsync((char*)dst.p[pl] + off, (const char*)src[pl] + off, n, kind, stream));
         }
     }
+    return LUZRT_OK;
+}
+} // namespace
+
+int luzrt_set_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, const void* material,
+                      const void* emission, const void* depth, int src_is_device) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    const void* src[5] = {albedo, normal, material, emission, depth};
+    return copy_gbuffer(c, GbufPlanes{{c->albedo, c->normal, c->material, c->emission, c->depth}}, src,
+                        src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream);
+}
+
+int luzrt_prefetch_gbuffer(luzrt_ctx* c, const void* albedo, const void* normal, const void* material,
+                           const void* emission, const void* depth) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    REQUIRE(c, albedo && normal && material && emission && depth, "all five planes are required");
+    DeviceGuard g(c->device);
+    if (!c->upload_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_flip, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_uploaded, cudaEventDisableTiming));
+        CU(c, cudaEventRecord(c->ev_flip, c->stream));
+    }
+    if (!c->albedo_b) {
+        const size_t px = (size_t)c->w * c->h;
+        CU(c, cudaMalloc(&c->albedo_b, px * 4));
+        CU(c, cudaMalloc(&c->material_b, px * 4));
+        CU(c, cudaMalloc(&c->emission_b, px * 4));
+        CU(c, cudaMalloc(&c->normal_b, px * 16));
+        CU(c, cudaMalloc(&c->depth_b, px * 4));
+    }
+    // the back set was the front set until the last flip: its readers were all enqueued before ev_flip
+    CU(c, cudaStreamWaitEvent(c->upload_stream, c->ev_flip, 0));
+    const void* src[5] = {albedo, normal, material, emission, depth};
+    int rc = copy_gbuffer(c, GbufPlanes{{c->albedo_b, c->normal_b, c->material_b, c->emission_b, c->depth_b}}, src,
+                          cudaMemcpyHostToDevice, c->upload_stream);
+    if (rc != LUZRT_OK) return rc;
+    CU(c, cudaEventRecord(c->ev_uploaded, c->upload_stream));
+    c->upload_pending = true;
+    return LUZRT_OK;
+}
+
+int luzrt_flip_gbuffer(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->upload_pending) return fail(c, LUZRT_E_STATE, "luzrt_prefetch_gbuffer has not been called");
+    DeviceGuard g(c->device);
+    CU(c, cudaEventRecord(c->ev_flip, c->stream)); // everything enqueued so far read the old front set
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_uploaded, 0));
+    std::swap(c->albedo, c->albedo_b);
+    std::swap(c->normal, c->normal_b);
+    std::swap(c->material, c->material_b);
+    std::swap(c->emission, c->emission_b);
+    std::swap(c->depth, c->depth_b);
+    c->upload_pending = false;
+    return LUZRT_OK;
+}
+
+int luzrt_read_owned_async(luzrt_ctx* c, int which, void* dst, size_t bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, dst, "dst is null");
+    REQUIRE(c, is_light_image(which), "only the light images can be read asynchronously");
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    DeviceGuard g(c->device);
+    if (!c->download_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->download_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_result, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_downloaded, cudaEventDisableTiming));
+    }
+    size_t have = 0;
+    void* src = image_ptr(c, which, &have);
+    const size_t row = have / c->h, need = row * c->rows_per_rank;
+    REQUIRE(c, bytes >= need, "destination buffer too small");
+    CU(c, cudaEventRecord(c->ev_result, c->stream));
+    CU(c, cudaStreamWaitEvent(c->download_stream, c->ev_result, 0));
+    // a rank's own rows are contiguous in the banded storage order and are not written by a gather in flight
+    CU(c, cudaMemcpyAsync(dst, (const char*)src + row * c->rows_per_rank * (size_t)c->rank, need, cudaMemcpyDeviceToHost,
+                          c->download_stream));
+    CU(c, cudaEventRecord(c->ev_downloaded, c->download_stream));
+    c->download_pending = true;
+    return LUZRT_OK;
+}
+
+int luzrt_read_wait(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->download_pending) return LUZRT_OK;
+    DeviceGuard g(c->device);
+    CU(c, cudaEventSynchronize(c->ev_downloaded));
+    c->download_pending = false;
     return LUZRT_OK;
 }
 
@@ -830,6 +939,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
     CU(c, wait_gather(c, a.out));
+    if (c->download_pending) CU(c, cudaStreamWaitEvent(c->stream, c->ev_downloaded, 0)); // the image may be reused
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));

@@ -23,6 +23,7 @@ EXPORTS = [
     "luzrt_set_gbuffer", "luzrt_gbuffer_pass", "luzrt_set_debug", "luzrt_light_pass", "luzrt_taa_pass",
     "luzrt_gather", "luzrt_compose_pass", "luzrt_swap_light_history", "luzrt_read", "luzrt_device_ptr",
     "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_bands", "luzrt_read_owned",
+    "luzrt_prefetch_gbuffer", "luzrt_flip_gbuffer", "luzrt_read_owned_async", "luzrt_read_wait",
     "luzrt_probe_read_bandwidth",
 ]
 
@@ -76,6 +77,10 @@ def load_library():
         "luzrt_read_rows": (i32, [vp, i32, u32, u32, vp, C.c_size_t]),
         "luzrt_owned_bands": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "luzrt_read_owned": (i32, [vp, i32, vp, C.c_size_t]),
+        "luzrt_prefetch_gbuffer": (i32, [vp, vp, vp, vp, vp, vp]),
+        "luzrt_flip_gbuffer": (i32, [vp]),
+        "luzrt_read_owned_async": (i32, [vp, i32, vp, C.c_size_t]),
+        "luzrt_read_wait": (i32, [vp]),
         "luzrt_probe_read_bandwidth": (i32, [vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
     }
     for name, (res, args) in sig.items():
@@ -238,6 +243,18 @@ class LuzRT:
         v = [C.c_uint32() for _ in range(4)]
         self._ck(self.lib.luzrt_owned_bands(self.h, *[C.byref(x) for x in v]))
         return tuple(x.value for x in v)
+
+    def prefetch_gbuffer(self, albedo, normal, material, emission, depth):
+        self._ck(self.lib.luzrt_prefetch_gbuffer(self.h, _ptr(albedo), _ptr(normal), _ptr(material), _ptr(emission), _ptr(depth)))
+
+    def flip_gbuffer(self):
+        self._ck(self.lib.luzrt_flip_gbuffer(self.h))
+
+    def read_owned_async(self, which, out):
+        self._ck(self.lib.luzrt_read_owned_async(self.h, which, _ptr(out), out.nbytes))
+
+    def read_wait(self):
+        self._ck(self.lib.luzrt_read_wait(self.h))
 
     def read_owned(self, which, out):
         self._ck(self.lib.luzrt_read_owned(self.h, which, _ptr(out), out.nbytes))

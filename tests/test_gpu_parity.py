@@ -376,3 +376,59 @@ def test_banded_partition_matches_single_gpu(rt_factory):
             rt.read_rows(R.IMG_LIGHT, int(own[3]), int(own[3]) + 7, part)
             assert np.array_equal(part, full_res[int(own[3]):int(own[3]) + 7])
         assert rays == full_st.rays  # halo rows are recomputation, not frame rays
+
+
+def test_pipelined_host_path_matches_blocking_calls(rt_factory):
+    """luzrt_prefetch_gbuffer / luzrt_flip_gbuffer / luzrt_read_owned_async (copies overlapped with the previous
+    frame) must give bit-identical frames to luzrt_set_gbuffer / luzrt_read_owned, frame after frame."""
+    import torch
+    w, h = 320, 192
+    sc = S.synthetic_scene(w, h, grid=3, n_lights=2, light_samples=1, ao_samples=3)
+    world = O.World(sc["meshes"], sc["instances"])
+    gbs = []
+    for eye in ((9, 7, 11), (8.5, 7.2, 11.3), (8, 7.4, 11.6)):  # three different frames of input
+        s2 = S.synthetic_scene(w, h, grid=3, n_lights=2, light_samples=1, ao_samples=3, eye=eye)
+        gbs.append((s2, O.gbuffer_pass(s2["scene"], world, s2["models"], len(s2["instances"]), [], w, h, exhaustive=False)))
+    bn = S.blue_noise()
+
+    def setup():
+        rt = rt_factory()
+        rt.resize(w, h)
+        rt.set_blue_noise(bn)
+        S.make_rt_scene(rt, sc)
+        rt.set_debug(0)
+        return rt
+
+    ref_frames = []
+    rt = setup()
+    for i, (s2, gb) in enumerate(gbs):
+        rt.set_scene(s2["scene"])
+        rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
+        rt.light_pass(i)
+        rt.taa_pass(True)
+        out = np.zeros((h, w, 4), np.float32)
+        rt.read_owned(R.IMG_LIGHT, out)
+        rt.swap_light_history()
+        ref_frames.append(out)
+
+    rt = setup()
+    pinned = [[torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
+               (gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)] for _, gb in gbs]
+    outs = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in gbs]
+    rt.prefetch_gbuffer(*[t.numpy() for t in pinned[0]])
+    for i, (s2, gb) in enumerate(gbs):
+        rt.set_scene(s2["scene"])
+        rt.flip_gbuffer()
+        rt.light_pass(i)
+        rt.taa_pass(True)
+        rt.read_wait()
+        rt.read_owned_async(R.IMG_LIGHT, outs[i].numpy())
+        rt.swap_light_history()
+        if i + 1 < len(gbs):
+            rt.prefetch_gbuffer(*[t.numpy() for t in pinned[i + 1]])
+    rt.read_wait()
+    rt.sync()
+    for i in range(len(gbs)):
+        assert np.array_equal(outs[i].numpy(), ref_frames[i]), "frame %d differs" % i
+    with pytest.raises(R.LuzError):
+        rt.flip_gbuffer()  # nothing prefetched
