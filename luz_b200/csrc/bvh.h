@@ -30,11 +30,13 @@ struct BuildScratch {
     void* mem = nullptr;
     size_t bytes = 0;
     uint64_t* host_pair = nullptr; // pinned, 2 x u64
+    uint32_t* host_levels = nullptr; // pinned level table of the single-CTA collapse
     ~BuildScratch();
 };
 
 // Builds a WideBvh over n boxes (device pointer).  max_leaf = primitives per leaf slot (3 for
-// triangles, 1 for instances).  Deterministic.  Synchronises the stream once per tree level.
+// triangles, 1 for instances).  Deterministic.  Synchronises the stream once (trees of up to 2^17
+// primitives: TLAS rebuilds) or once per tree level (large meshes, built once).
 // Returns cudaSuccess or the failing CUDA error.  *launches counts kernels launched.
 cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const BoxF* d_boxes, uint32_t n,
                            uint32_t max_leaf, WideBvh& out, uint64_t* launches);

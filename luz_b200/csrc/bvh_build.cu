@@ -3,13 +3,15 @@
 // Replaces the driver-side vkCmdBuildAccelerationStructuresKHR that the reference reaches through
 // vkw::CmdBuildBLAS / vkw::CmdBuildTLAS (source/Graphics/VulkanWrapper.cpp:1089-1104, :1106-1139).
 // Pipeline: centroid bounds -> 30-bit Morton codes -> stable LSD radix sort (own kernels) ->
-// Karras LBVH (index tie-break for duplicate codes) -> bottom-up boxes -> level-synchronous
-// greedy collapse to 8-wide nodes with prefix-sum allocation (no allocation atomics, so the
-// node/primitive layout is identical on every run and every GPU) -> 80-byte quantised nodes.
+// Karras LBVH (index tie-break for duplicate codes) -> bottom-up boxes + SAH cost tables ->
+// level-synchronous optimal collapse to 8-wide nodes (Ylitie et al. 2017 dynamic programme) with
+// prefix-sum allocation (no allocation atomics, so the node/primitive layout is identical on every
+// run and every GPU).  Small trees (TLAS rebuilds) are collapsed by one CTA without host round trips.
 #include "bvh.h"
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace luz {
 
@@ -262,9 +264,69 @@ __device__ __forceinline__ BoxF load_box_cg(const BoxF* p) {
     return r;
 }
 
+// ---- optimal collapse: cost tables (Ylitie, Karras, Laine 2017, section 3) ----------------------------
+// For a binary node n and a budget i of 1..7 slots of a wide node, C(n, i) is the cheapest SAH cost of
+// representing n's subtree by at most i slots (each a leaf slot of <= max_leaf primitives or an
+// internal child node, which in turn distributes 8 slots):
+//   C_leaf(n) = A(n) * P(n) * c_prim            if P(n) <= max_leaf, else infinity
+//   D(n, j)   = min_{0<k<j} C(left, k) + C(right, j-k)
+//   C(n, 1)   = min(C_leaf(n), D(n, 8) + A(n) * c_node)
+//   C(n, i)   = min(D(n, i), C(n, i-1))
+// cost[8n + 0] holds C_leaf(n), cost[8n + i] holds C(n, i).  A single primitive costs A * c_prim whatever
+// the budget.  Every value is a min over plain fp32 sums evaluated in one fixed order, so the plan step
+// below re-derives the arg-mins bit-exactly and the tree is identical on every run and every GPU.
+struct CostParams {
+    float c_node, c_prim;
+    uint32_t max_leaf;
+};
+
+__device__ __forceinline__ float box_area(const BoxF b) {
+    const float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
+    const float a = dx * dy + dy * dz + dz * dx;
+    return a >= 0.0f ? a : 0.0f; // NaN boxes cost nothing
+}
+
+__device__ __forceinline__ void distribute_costs(const float* cl, const float* cr, float* dist /*[9], 2..8 used*/) {
+#pragma unroll
+    for (int j = 2; j <= 8; j++) {
+        float d = INFINITY;
+#pragma unroll
+        for (int k = 1; k <= 7; k++)
+            if (k < j && j - k <= 7) d = fminf(d, cl[k] + cr[j - k]);
+        dist[j] = d;
+    }
+}
+
+__device__ __forceinline__ void node_costs(const float* cl, const float* cr, const float area, const uint32_t count,
+                                           const CostParams p, float* c /*[8]*/) {
+    float dist[9];
+    distribute_costs(cl, cr, dist);
+    c[0] = count <= p.max_leaf ? area * (float)count * p.c_prim : INFINITY;
+    c[1] = fminf(c[0], dist[8] + area * p.c_node);
+#pragma unroll
+    for (int i = 2; i <= 7; i++) c[i] = fminf(dist[i], c[i - 1]);
+}
+
+template <bool CG>
+__device__ __forceinline__ void load_costs(const float* __restrict__ cost, const BoxF* __restrict__ box, const int n,
+                                           const uint32_t ref, const float c_prim, float* c /*[8]*/) {
+    if (ref >= (uint32_t)(n - 1)) {
+        const float a = box_area(CG ? load_box_cg(&box[ref]) : box[ref]) * c_prim;
+#pragma unroll
+        for (int i = 0; i < 8; i++) c[i] = a;
+    } else {
+        const float4* p4 = reinterpret_cast<const float4*>(cost) + 2 * (size_t)ref;
+        const float4 a = CG ? __ldcg(p4) : p4[0], b = CG ? __ldcg(p4 + 1) : p4[1];
+        c[0] = a.x, c[1] = a.y, c[2] = a.z, c[3] = a.w, c[4] = b.x, c[5] = b.y, c[6] = b.z, c[7] = b.w;
+    }
+}
+
+// bottom-up: boxes and cost tables of the binary tree (the last of the two children to arrive continues)
 __global__ void k_fit(const BoxF* __restrict__ prim_boxes, const uint32_t* __restrict__ sorted_idx, int n,
                       const uint32_t* __restrict__ left, const uint32_t* __restrict__ right,
-                      const uint32_t* __restrict__ parent, uint32_t* __restrict__ flags, BoxF* __restrict__ box) {
+                      const uint32_t* __restrict__ first, const uint32_t* __restrict__ last,
+                      const uint32_t* __restrict__ parent, uint32_t* __restrict__ flags, BoxF* __restrict__ box,
+                      float* __restrict__ cost, const CostParams cp) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     box[n - 1 + k] = prim_boxes[sorted_idx[k]];
@@ -275,8 +337,17 @@ __global__ void k_fit(const BoxF* __restrict__ prim_boxes, const uint32_t* __res
         const uint32_t old = atomicAdd(&flags[cur], 1u);
         if (old == 0) return; // the sibling subtree is not finished: its thread will continue
         __threadfence();
-        const BoxF a = load_box_cg(&box[left[cur]]), b = load_box_cg(&box[right[cur]]);
-        box[cur] = box_union(a, b);
+        const uint32_t l = left[cur], r = right[cur];
+        const BoxF a = load_box_cg(&box[l]), b = load_box_cg(&box[r]);
+        const BoxF u = box_union(a, b);
+        box[cur] = u;
+        float cl[8], cr[8], c[8];
+        load_costs<true>(cost, box, n, l, cp.c_prim, cl);
+        load_costs<true>(cost, box, n, r, cp.c_prim, cr);
+        node_costs(cl, cr, box_area(u), last[cur] - first[cur] + 1u, cp, c);
+        float4* dst = reinterpret_cast<float4*>(cost) + 2 * (size_t)cur;
+        dst[0] = make_float4(c[0], c[1], c[2], c[3]);
+        dst[1] = make_float4(c[4], c[5], c[6], c[7]);
         __threadfence();
         cur = parent[cur];
     }
@@ -297,63 +368,85 @@ __device__ __forceinline__ uint32_t ref_count(const Tree2& t, uint32_t ref) {
 __device__ __forceinline__ uint32_t ref_first(const Tree2& t, uint32_t ref) {
     return ref >= (uint32_t)(t.n - 1) ? ref - (uint32_t)(t.n - 1) : t.first[ref];
 }
-__device__ __forceinline__ float box_area(const BoxF b) {
-    const float dx = b.hix - b.lox, dy = b.hiy - b.loy, dz = b.hiz - b.loz;
-    const float a = dx * dy + dy * dz + dz * dx;
-    return a >= 0.0f ? a : 0.0f; // NaN boxes sort last among expandable slots
-}
-// expansion priority of a slot: -1 for leaf slots (never expanded), else the surface area
-__device__ __forceinline__ float slot_area(const Tree2& t, uint32_t ref, uint32_t max_leaf) {
-    return ref_count(t, ref) <= max_leaf ? -1.0f : box_area(t.box[ref]);
+constexpr uint32_t kSlotInternal = 0x80000000u; // flag on a planned slot: the subtree becomes a child node
+
+// Chooses the (at most 8) slots of the wide node rooted at binary node r by following the arg-mins of the
+// cost tables, left subtree first (so the slots are in Morton order).  s[k] = binary ref | kSlotInternal.
+// Returns the slot count; *counts = (#leaf primitives << 32) | #internal children.
+__device__ __forceinline__ int plan_slots(const Tree2& t, const float* __restrict__ cost, const uint32_t r,
+                                          const CostParams p, uint32_t* s, uint64_t* counts) {
+    int ns = 0;
+    uint32_t n_int = 0, n_prim = 0;
+    if (r >= (uint32_t)(t.n - 1)) { // a tree of one primitive: the root holds it in its only slot
+        s[0] = r;
+        *counts = 1ull << 32;
+        return 1;
+    }
+    uint32_t st_ref[8];
+    int st_budget[8];
+    int sp = 0;
+    st_ref[sp] = r;
+    st_budget[sp++] = 8;
+    while (sp) {
+        const uint32_t ref = st_ref[--sp];
+        int i = st_budget[sp];
+        if (ref >= (uint32_t)(t.n - 1)) { // a single primitive
+            s[ns++] = ref;
+            n_prim++;
+            continue;
+        }
+        if (i < 8) {
+            float c[8];
+            load_costs<false>(cost, t.box, t.n, ref, p.c_prim, c);
+            while (i > 1 && c[i] == c[i - 1]) i--;
+            if (i == 1) {
+                const uint32_t cnt = ref_count(t, ref);
+                if (cnt <= p.max_leaf && c[0] <= c[1]) {
+                    s[ns++] = ref;
+                    n_prim += cnt;
+                } else {
+                    s[ns++] = ref | kSlotInternal;
+                    n_int++;
+                }
+                continue;
+            }
+        }
+        // split the budget i between the two children: first k reaching the minimum wins
+        const uint32_t l = t.left[ref], rr = t.right[ref];
+        float cl[8], cr[8];
+        load_costs<false>(cost, t.box, t.n, l, p.c_prim, cl);
+        load_costs<false>(cost, t.box, t.n, rr, p.c_prim, cr);
+        float best = INFINITY;
+        int bk = 1;
+        for (int k = 1; k <= 7; k++)
+            if (k < i && i - k <= 7) {
+                const float v = cl[k] + cr[i - k];
+                if (v < best) {
+                    best = v;
+                    bk = k;
+                }
+            }
+        if (i - bk > 7) bk = i - 7; // all-infinite tables: any feasible split
+        st_ref[sp] = rr;
+        st_budget[sp++] = i - bk;
+        st_ref[sp] = l;
+        st_budget[sp++] = bk;
+    }
+    *counts = ((uint64_t)n_prim << 32) | n_int;
+    return ns;
 }
 
 // plan: per level item, choose up to 8 slots; counts[i] = (#leaf primitives << 32) | #internal children
-__global__ void k_collapse_plan(Tree2 t, const uint32_t* __restrict__ items, uint32_t n_items, uint32_t max_leaf,
-                                uint32_t* __restrict__ slots, uint64_t* __restrict__ counts) {
+__global__ void k_collapse_plan(Tree2 t, const float* __restrict__ cost, const uint32_t* __restrict__ items,
+                                uint32_t n_items, CostParams p, uint32_t* __restrict__ slots,
+                                uint64_t* __restrict__ counts) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
-    const uint32_t r = items[i];
     uint32_t s[8];
-    float area[8];
-    int ns;
-    if (ref_count(t, r) <= max_leaf) { // only the root of a tiny tree
-        s[0] = r;
-        area[0] = -1.0f;
-        ns = 1;
-    } else {
-        s[0] = t.left[r];
-        s[1] = t.right[r];
-        ns = 2;
-        for (int k = 0; k < 2; k++) area[k] = slot_area(t, s[k], max_leaf);
-        while (ns < 8) {
-            int best = -1;
-            float ba = -1.0f;
-            for (int k = 0; k < ns; k++) // largest surface first; leaves carry area -1; first wins ties
-                if (area[k] > ba) {
-                    ba = area[k];
-                    best = k;
-                }
-            if (best < 0) break;
-            const uint32_t e = s[best];
-            const uint32_t a = t.left[e], b = t.right[e];
-            s[best] = a;
-            area[best] = slot_area(t, a, max_leaf);
-            s[ns] = b;
-            area[ns] = slot_area(t, b, max_leaf);
-            ns++;
-        }
-    }
-    uint32_t n_int = 0, n_prim = 0;
-    for (int k = 0; k < 8; k++) {
-        if (k < ns) {
-            slots[i * 8 + k] = s[k];
-            if (area[k] >= 0.0f) n_int++;
-            else n_prim += ref_count(t, s[k]);
-        } else {
-            slots[i * 8 + k] = kNone;
-        }
-    }
-    counts[i] = ((uint64_t)n_prim << 32) | n_int;
+    uint64_t cnt;
+    const int ns = plan_slots(t, cost, items[i], p, s, &cnt);
+    for (int k = 0; k < 8; k++) slots[i * 8 + k] = k < ns ? s[k] : kNone;
+    counts[i] = cnt;
 }
 
 // exponent byte e such that 255 * 2^(e-127) >= ext
@@ -427,17 +520,13 @@ __device__ __forceinline__ void write_node(WideNode* dst, const BoxF nb, const u
     for (int k = 0; k < 5; k++) d4[k] = src[k];
 }
 
-__global__ void k_collapse_emit(Tree2 t, const uint32_t* __restrict__ items, uint32_t n_items, uint32_t max_leaf,
-                                const uint32_t* __restrict__ slots, const uint64_t* __restrict__ scanned,
-                                uint32_t level_start, uint32_t next_level_start, uint32_t prim_cursor,
-                                const uint32_t* __restrict__ sorted_idx, WideNode* __restrict__ nodes,
-                                BoxF* __restrict__ node_bounds, uint32_t* __restrict__ prim_order,
-                                uint32_t* __restrict__ next_items) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_items) return;
-    const uint32_t r = items[i];
-    const uint64_t sc = scanned[i];
-    const uint32_t int_off = (uint32_t)(sc & 0xFFFFFFFFull), prim_off = (uint32_t)(sc >> 32);
+// Writes the wide node planned as s[0..8) (item i of its level) and queues its internal children.
+__device__ __forceinline__ void emit_node(const Tree2& t, const uint32_t r, const uint32_t* s, const uint32_t int_off,
+                                          const uint32_t prim_off, const uint32_t node_index,
+                                          const uint32_t next_level_start, const uint32_t prim_cursor,
+                                          const uint32_t* __restrict__ sorted_idx, WideNode* __restrict__ nodes,
+                                          BoxF* __restrict__ node_bounds, uint32_t* __restrict__ prim_order,
+                                          uint32_t* __restrict__ next_items) {
     const uint32_t child_base = next_level_start + int_off;
     const uint32_t prim_base = prim_cursor + prim_off;
     uint8_t meta[8];
@@ -446,15 +535,15 @@ __global__ void k_collapse_emit(Tree2 t, const uint32_t* __restrict__ items, uin
     uint8_t imask = 0;
     uint32_t n_int = 0, poff = 0;
     for (int k = 0; k < 8; k++) {
-        const uint32_t s = slots[i * 8 + k];
         meta[k] = 0;
         used[k] = false;
-        if (s == kNone) continue;
+        if (s[k] == kNone) continue;
+        const uint32_t ref = s[k] & ~kSlotInternal;
         used[k] = true;
-        cb[k] = t.box[s];
-        const uint32_t cnt = ref_count(t, s);
-        if (cnt <= max_leaf) {
-            const uint32_t f = ref_first(t, s);
+        cb[k] = t.box[ref];
+        if (!(s[k] & kSlotInternal)) {
+            const uint32_t cnt = ref_count(t, ref);
+            const uint32_t f = ref_first(t, ref);
             for (uint32_t q = 0; q < cnt; q++) prim_order[prim_base + poff + q] = sorted_idx[f + q];
             const uint32_t unary = (1u << cnt) - 1u; // 1 -> 001, 2 -> 011, 3 -> 111
             meta[k] = (uint8_t)((unary << 5) | poff);
@@ -462,13 +551,110 @@ __global__ void k_collapse_emit(Tree2 t, const uint32_t* __restrict__ items, uin
         } else {
             meta[k] = (uint8_t)((1u << 5) | (24u + (uint32_t)k));
             imask |= (uint8_t)(1u << k);
-            next_items[int_off + n_int] = s;
+            next_items[int_off + n_int] = ref;
             n_int++;
         }
     }
     const BoxF nb = t.box[r];
-    node_bounds[level_start + i] = nb;
-    write_node(nodes + level_start + i, nb, child_base, prim_base, meta, imask, cb, used);
+    node_bounds[node_index] = nb;
+    write_node(nodes + node_index, nb, child_base, prim_base, meta, imask, cb, used);
+}
+
+__global__ void k_collapse_emit(Tree2 t, const uint32_t* __restrict__ items, uint32_t n_items,
+                                const uint32_t* __restrict__ slots, const uint64_t* __restrict__ scanned,
+                                uint32_t level_start, uint32_t next_level_start, uint32_t prim_cursor,
+                                const uint32_t* __restrict__ sorted_idx, WideNode* __restrict__ nodes,
+                                BoxF* __restrict__ node_bounds, uint32_t* __restrict__ prim_order,
+                                uint32_t* __restrict__ next_items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    uint32_t s[8];
+    for (int k = 0; k < 8; k++) s[k] = slots[i * 8 + k];
+    const uint64_t sc = scanned[i];
+    emit_node(t, items[i], s, (uint32_t)(sc & 0xFFFFFFFFull), (uint32_t)(sc >> 32), level_start + i, next_level_start,
+              prim_cursor, sorted_idx, nodes, node_bounds, prim_order, next_items);
+}
+
+// The whole collapse of a small tree (TLAS rebuilds, small meshes) by one CTA: the level loop, the prefix
+// sums that allocate child nodes and leaf primitives, and the level table stay on the device, so a rebuild
+// costs no host round trip per level.  level_table: [0] = #levels, [1] = #nodes, [2] = error flag,
+// [4 + 2l] = first node of level l, [5 + 2l] = node count.
+constexpr int kSmallThreads = 1024;
+constexpr uint32_t kMaxLevels = 60;
+__global__ void __launch_bounds__(kSmallThreads) k_collapse_small(Tree2 t, const float* __restrict__ cost, CostParams p,
+                                                               const uint32_t* __restrict__ sorted_idx,
+                                                               WideNode* __restrict__ nodes, BoxF* __restrict__ node_bounds,
+                                                               uint32_t* __restrict__ prim_order, uint32_t* items,
+                                                               uint32_t* next_items, uint32_t node_capacity,
+                                                               uint32_t* __restrict__ level_table) {
+    __shared__ uint64_t warp_sums[32];
+    __shared__ uint64_t carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) items[0] = 0; // the root of the binary tree (internal node 0, or leaf 0 when n == 1)
+    uint32_t level_start = 0, level_count = 1, prim_cursor = 0, level = 0, err = 0;
+    while (level_count) {
+        if (threadIdx.x == 0) carry = 0;
+        __syncthreads();
+        const uint32_t next_start = level_start + level_count;
+        for (uint32_t base = 0; base < level_count; base += kSmallThreads) {
+            const uint32_t i = base + threadIdx.x;
+            const bool valid = i < level_count;
+            uint32_t s[8];
+            uint64_t v = 0;
+            uint32_t r = 0;
+            if (valid) {
+                r = items[i];
+                const int ns = plan_slots(t, cost, r, p, s, &v);
+                for (int k = ns; k < 8; k++) s[k] = kNone;
+            }
+            uint64_t x = v;
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+                if (lane >= off) x += y;
+            }
+            if (lane == 31) warp_sums[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                uint64_t w = warp_sums[lane];
+                for (int off = 1; off < 32; off <<= 1) {
+                    const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, w, off);
+                    if (lane >= off) w += y;
+                }
+                warp_sums[lane] = w; // inclusive over warps
+            }
+            __syncthreads();
+            const uint64_t c = carry;
+            const uint64_t excl = c + (warp ? warp_sums[warp - 1] : 0ull) + x - v;
+            if (valid)
+                emit_node(t, r, s, (uint32_t)(excl & 0xFFFFFFFFull), (uint32_t)(excl >> 32), level_start + i, next_start,
+                          prim_cursor, sorted_idx, nodes, node_bounds, prim_order, next_items);
+            __syncthreads();
+            if (threadIdx.x == kSmallThreads - 1) carry = excl + v;
+            __syncthreads();
+        }
+        const uint64_t tot = carry;
+        if (threadIdx.x == 0 && level < kMaxLevels) {
+            level_table[4 + 2 * level] = level_start;
+            level_table[5 + 2 * level] = level_count;
+        }
+        level++;
+        level_start = next_start;
+        level_count = (uint32_t)(tot & 0xFFFFFFFFull);
+        prim_cursor += (uint32_t)(tot >> 32);
+        uint32_t* tmp = items;
+        items = next_items;
+        next_items = tmp;
+        if ((size_t)level_start + level_count > node_capacity || level >= kMaxLevels) {
+            err = 1;
+            break;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        level_table[0] = level;
+        level_table[1] = level_start;
+        level_table[2] = err;
+    }
 }
 
 __global__ void k_empty_root(WideNode* nodes, BoxF* node_bounds) {
@@ -641,6 +827,25 @@ struct Carver {
     }
 };
 
+// trees up to this many primitives are collapsed by the single-CTA kernel
+constexpr uint32_t kSmallBuild = 1u << 17;
+
+// SAH constants of the collapse, in units of one wide-node visit.  A leaf slot is tested triangle by
+// triangle by few lanes of a warp (profiles/r1_light_pass_v4.md: 3.6 active lanes in the triangle test vs
+// 20.6 in the node test), which is why a primitive is priced above the textbook 0.3.  LUZRT_BVH_CPRIM /
+// LUZRT_BVH_CPRIM_TLAS override them for tuning runs.
+CostParams cost_params(uint32_t max_leaf) {
+    static const float c_prim_tri = [] {
+        const char* e = getenv("LUZRT_BVH_CPRIM");
+        return e ? (float)atof(e) : 0.6f;
+    }();
+    static const float c_prim_inst = [] {
+        const char* e = getenv("LUZRT_BVH_CPRIM_TLAS");
+        return e ? (float)atof(e) : 2.0f;
+    }();
+    return CostParams{1.0f, max_leaf > 1 ? c_prim_tri : c_prim_inst, max_leaf};
+}
+
 cudaError_t ensure_capacity(WideBvh& out, size_t nodes, size_t prims) {
     if (out.node_capacity < nodes) {
         if (out.nodes) cudaFree(out.nodes);
@@ -667,6 +872,7 @@ cudaError_t ensure_capacity(WideBvh& out, size_t nodes, size_t prims) {
 BuildScratch::~BuildScratch() {
     if (mem) cudaFree(mem);
     if (host_pair) cudaFreeHost(host_pair);
+    if (host_levels) cudaFreeHost(host_levels);
 }
 
 void free_wide_bvh(WideBvh& b) {
@@ -682,6 +888,7 @@ cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const Box
     out.levels.clear();
     out.n_prims = n;
     if (!scratch.host_pair) LUZ_CK(cudaMallocHost(&scratch.host_pair, 2 * sizeof(uint64_t)));
+    if (!scratch.host_levels) LUZ_CK(cudaMallocHost(&scratch.host_levels, sizeof(uint32_t) * (4 + 2 * kMaxLevels)));
     if (n == 0) {
         LUZ_CK(ensure_capacity(out, 1, 1));
         k_empty_root<<<1, 1, 0, stream>>>(out.nodes, out.node_bounds);
@@ -714,6 +921,8 @@ cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const Box
         c.take<uint32_t>(n);
         c.take<uint32_t>(n);
         c.take<uint32_t>(8 * (size_t)n);
+        c.take<float>(8 * (size_t)n);
+        c.take<uint32_t>(4 + 2 * kMaxLevels);
         need = c.off + 256;
     }
     if (scratch.bytes < need) {
@@ -744,6 +953,9 @@ cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const Box
     uint32_t* items_a = c.take<uint32_t>(n);
     uint32_t* items_b = c.take<uint32_t>(n);
     uint32_t* slots = c.take<uint32_t>(8 * (size_t)n);
+    float* cost = c.take<float>(8 * (size_t)n);
+    uint32_t* level_table = c.take<uint32_t>(4 + 2 * kMaxLevels);
+    const CostParams cp = cost_params(max_leaf);
 
     const int T = 256;
     k_init_bounds<<<1, 32, 0, stream>>>(d_bounds);
@@ -769,24 +981,39 @@ cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const Box
         LUZ_CK(cudaMemsetAsync(flags, 0, sizeof(uint32_t) * n, stream));
         nl += 1;
     }
-    k_fit<<<div_up(n, T), T, 0, stream>>>(d_boxes, vin, (int)n, left, right, parent, flags, box);
+    k_fit<<<div_up(n, T), T, 0, stream>>>(d_boxes, vin, (int)n, left, right, first, last, parent, flags, box, cost, cp);
     nl += 1;
 
     Tree2 tree{left, right, first, last, box, (int)n};
+    if (n <= kSmallBuild) {
+        // one CTA runs every level; a single read-back of the level table at the end (the host needs the
+        // node count and the per-level ranges for refits and for the stack-depth check)
+        k_collapse_small<<<1, kSmallThreads, 0, stream>>>(tree, cost, cp, vin, out.nodes, out.node_bounds, out.prim_order,
+                                                          items_a, items_b, (uint32_t)std::min<size_t>(out.node_capacity, 0xFFFFFFFFu),
+                                                          level_table);
+        nl += 1;
+        LUZ_CK(cudaMemcpyAsync(scratch.host_levels, level_table, sizeof(uint32_t) * (4 + 2 * kMaxLevels),
+                               cudaMemcpyDeviceToHost, stream));
+        LUZ_CK(cudaStreamSynchronize(stream));
+        const uint32_t* lt = scratch.host_levels;
+        if (lt[2]) return cudaErrorMemoryAllocation;
+        for (uint32_t l = 0; l < lt[0]; l++) out.levels.push_back(make_uint2(lt[4 + 2 * l], lt[5 + 2 * l]));
+        out.n_nodes = lt[1];
+        if (launches) *launches += nl;
+        return cudaGetLastError();
+    }
     // level 0 = the root of the binary tree (internal node 0, or leaf 0 when n == 1)
     const uint32_t root_ref = 0;
     LUZ_CK(cudaMemcpyAsync(items_a, &root_ref, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
     uint32_t *items = items_a, *next_items = items_b;
     uint32_t level_start = 0, level_count = 1, prim_cursor = 0;
     while (level_count) {
-        k_collapse_plan<<<div_up(level_count, 128), 128, 0, stream>>>(tree, items, level_count, max_leaf, slots,
-                                                                      tmp64_a);
+        k_collapse_plan<<<div_up(level_count, 128), 128, 0, stream>>>(tree, cost, items, level_count, cp, slots, tmp64_a);
         k_scan_u64<<<1, 1024, 0, stream>>>(tmp64_a, tmp64_b, level_count, d_total);
         const uint32_t next_start = level_start + level_count;
-        k_collapse_emit<<<div_up(level_count, 128), 128, 0, stream>>>(tree, items, level_count, max_leaf, slots,
-                                                                      tmp64_b, level_start, next_start, prim_cursor,
-                                                                      vin, out.nodes, out.node_bounds, out.prim_order,
-                                                                      next_items);
+        k_collapse_emit<<<div_up(level_count, 128), 128, 0, stream>>>(tree, items, level_count, slots, tmp64_b, level_start,
+                                                                      next_start, prim_cursor, vin, out.nodes,
+                                                                      out.node_bounds, out.prim_order, next_items);
         nl += 3;
         LUZ_CK(cudaMemcpyAsync(scratch.host_pair, d_total, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
         LUZ_CK(cudaStreamSynchronize(stream));
