@@ -870,7 +870,7 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     }
     GbufferArgs a{};
     a.fc = c->fc;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u, c->min_node_lanes};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, c->min_node_lanes};
     a.inst_meta = c->d_meta;
     a.blas_attr = c->d_blas_attr;
     a.models = c->d_models;
@@ -928,7 +928,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.blue_noise = c->blue_noise;
     a.lights = c->d_lights;
     a.out = c->lightA;
-    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, 0x3F800000u, c->min_node_lanes};
+    a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, c->min_node_lanes};
     a.rows = shade_bands(c); // own bands plus the row above and below each (wrapping) that TAA's 3x3 taps read
     a.shadow_mask = c->d_shadow_mask;
     a.shadow_words = (uint32_t)c->shadow_mask_words;

@@ -449,75 +449,26 @@ __global__ void k_collapse_plan(Tree2 t, const float* __restrict__ cost, const u
     counts[i] = cnt;
 }
 
-// exponent byte e such that 255 * 2^(e-127) >= ext
-__device__ __forceinline__ uint32_t grid_exponent(float ext) {
-    const float s = ext / 255.0f;
-    const uint32_t bits = __float_as_uint(s);
-    uint32_t e = (bits >> 23) & 0xFFu;
-    if (bits & 0x7FFFFFu) e++;
-    e = max(e, 24u); // keep 2^(e-127) a normal number with headroom
-    e = min(e, 254u);
-    // guard against the rounding of ext/255
-    if (255.0f * __uint_as_float(e << 23) < ext) e = min(e + 1u, 254u);
-    return e;
-}
-
-__device__ __forceinline__ void quantize_box(const BoxF node, const uint32_t ex, const uint32_t ey, const uint32_t ez,
-                                             const BoxF c, uint8_t* q /* lox,loy,loz,hix,hiy,hiz */) {
-    const float sx = __uint_as_float(ex << 23), sy = __uint_as_float(ey << 23), sz = __uint_as_float(ez << 23);
-    const float lo[3] = {(c.lox - node.lox) / sx, (c.loy - node.loy) / sy, (c.loz - node.loz) / sz};
-    const float hi[3] = {(c.hix - node.lox) / sx, (c.hiy - node.loy) / sy, (c.hiz - node.loz) / sz};
-    const float sc[3] = {sx, sy, sz};
-    const float org[3] = {node.lox, node.loy, node.loz};
-    const float clo[3] = {c.lox, c.loy, c.loz}, chi[3] = {c.hix, c.hiy, c.hiz};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float ql = fminf(fmaxf(floorf(lo[k]), 0.0f), 255.0f);
-        float qh = fminf(fmaxf(ceilf(hi[k]), 0.0f), 255.0f);
-        // conservative after rounding of the dequantised corner
-        if (ql > 0.0f && org[k] + ql * sc[k] > clo[k]) ql -= 1.0f;
-        if (qh < 255.0f && org[k] + qh * sc[k] < chi[k]) qh += 1.0f;
-        q[k] = (uint8_t)ql;
-        q[3 + k] = (uint8_t)qh;
-    }
-}
-
-__device__ __forceinline__ void write_node(WideNode* dst, const BoxF nb, const uint32_t child_base,
-                                           const uint32_t prim_base, const uint8_t* meta, const uint8_t imask,
-                                           const BoxF* cb, const bool* used) {
+__device__ __forceinline__ void write_node(WideNode* dst, const uint32_t child_base, const uint32_t prim_base,
+                                           const uint8_t* meta, const uint8_t imask, const BoxF* cb, const bool* used) {
     WideNode w;
-    const uint32_t ex = grid_exponent(nb.hix - nb.lox), ey = grid_exponent(nb.hiy - nb.loy),
-                   ez = grid_exponent(nb.hiz - nb.loz);
-    w.px = nb.lox;
-    w.py = nb.loy;
-    w.pz = nb.loz;
-    w.ex = (uint8_t)ex;
-    w.ey = (uint8_t)ey;
-    w.ez = (uint8_t)ez;
-    w.imask = imask;
-    w.child_base = child_base;
+    w.child_base_imask = (child_base & 0x00FFFFFFu) | ((uint32_t)imask << 24);
     w.prim_base = prim_base;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         w.meta[k] = meta[k];
-        if (used[k]) {
-            uint8_t q[6];
-            quantize_box(nb, ex, ey, ez, cb[k], q);
-            w.qlox[k] = q[0];
-            w.qloy[k] = q[1];
-            w.qloz[k] = q[2];
-            w.qhix[k] = q[3];
-            w.qhiy[k] = q[4];
-            w.qhiz[k] = q[5];
-        } else { // inverted box: never hit
-            w.qlox[k] = w.qloy[k] = w.qloz[k] = 255;
-            w.qhix[k] = w.qhiy[k] = w.qhiz[k] = 0;
-        }
+        const bool u = used[k];
+        w.lox[k] = u ? cb[k].lox : INFINITY;
+        w.loy[k] = u ? cb[k].loy : INFINITY;
+        w.loz[k] = u ? cb[k].loz : INFINITY;
+        w.hix[k] = u ? cb[k].hix : -INFINITY;
+        w.hiy[k] = u ? cb[k].hiy : -INFINITY;
+        w.hiz[k] = u ? cb[k].hiz : -INFINITY;
     }
     const uint4* src = reinterpret_cast<const uint4*>(&w);
     uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-    for (int k = 0; k < 5; k++) d4[k] = src[k];
+    for (int k = 0; k < (int)(sizeof(WideNode) / 16); k++) d4[k] = src[k];
 }
 
 // Writes the wide node planned as s[0..8) (item i of its level) and queues its internal children.
@@ -557,7 +508,7 @@ __device__ __forceinline__ void emit_node(const Tree2& t, const uint32_t r, cons
     }
     const BoxF nb = t.box[r];
     node_bounds[node_index] = nb;
-    write_node(nodes + node_index, nb, child_base, prim_base, meta, imask, cb, used);
+    write_node(nodes + node_index, child_base, prim_base, meta, imask, cb, used);
 }
 
 __global__ void k_collapse_emit(Tree2 t, const uint32_t* __restrict__ items, uint32_t n_items,
@@ -644,7 +595,8 @@ __global__ void __launch_bounds__(kSmallThreads) k_collapse_small(Tree2 t, const
         uint32_t* tmp = items;
         items = next_items;
         next_items = tmp;
-        if ((size_t)level_start + level_count > node_capacity || level >= kMaxLevels) {
+        if ((size_t)level_start + level_count > node_capacity || level >= kMaxLevels ||
+            (size_t)level_start + level_count > kMaxWideNodes) {
             err = 1;
             break;
         }
@@ -663,7 +615,7 @@ __global__ void k_empty_root(WideNode* nodes, BoxF* node_bounds) {
     BoxF cb[8];
     BoxF nb = {0, 0, 0, 0, 0, 0};
     node_bounds[0] = nb;
-    write_node(nodes, nb, 0, 0, meta, 0, cb, used);
+    write_node(nodes, 0, 0, meta, 0, cb, used);
 }
 
 // refit one level: every node rebuilds its child boxes from leaf primitive boxes / child node bounds
@@ -673,25 +625,26 @@ __global__ void k_refit_level(WideNode* __restrict__ nodes, BoxF* __restrict__ n
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     WideNode* node = nodes + level_start + i;
-    const WideNode w = *node;
+    const uint4 hdr = *reinterpret_cast<const uint4*>(node);
+    const uint32_t child_base = hdr.x & 0x00FFFFFFu, imask = hdr.x >> 24, prim_base = hdr.y;
     uint8_t meta[8];
     bool used[8];
     BoxF cb[8];
     BoxF nb = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
     bool any = false;
     for (int k = 0; k < 8; k++) {
-        meta[k] = w.meta[k];
+        meta[k] = (uint8_t)(((k < 4 ? hdr.z : hdr.w) >> (8 * (k & 3))) & 0xFFu);
         used[k] = meta[k] != 0;
         if (!used[k]) continue;
         BoxF b;
-        if (w.imask & (1u << k)) {
-            const uint32_t rel = __popc((uint32_t)w.imask & ((1u << k) - 1u));
-            b = node_bounds[w.child_base + rel];
+        if (imask & (1u << k)) {
+            const uint32_t rel = __popc(imask & ((1u << k) - 1u));
+            b = node_bounds[child_base + rel];
         } else {
             const uint32_t off = meta[k] & 31u;
             const uint32_t cnt = __popc((uint32_t)(meta[k] >> 5));
-            b = prim_boxes[prim_order[w.prim_base + off]];
-            for (uint32_t q = 1; q < cnt; q++) b = box_union(b, prim_boxes[prim_order[w.prim_base + off + q]]);
+            b = prim_boxes[prim_order[prim_base + off]];
+            for (uint32_t q = 1; q < cnt; q++) b = box_union(b, prim_boxes[prim_order[prim_base + off + q]]);
         }
         cb[k] = b;
         nb = any ? box_union(nb, b) : b;
@@ -699,7 +652,7 @@ __global__ void k_refit_level(WideNode* __restrict__ nodes, BoxF* __restrict__ n
     }
     if (!any) nb = BoxF{0, 0, 0, 0, 0, 0};
     node_bounds[level_start + i] = nb;
-    write_node(node, nb, w.child_base, w.prim_base, meta, w.imask, cb, used);
+    write_node(node, child_base, prim_base, meta, (uint8_t)imask, cb, used);
 }
 
 // ---- mesh / instance helpers -------------------------------------------------------------------------
@@ -1024,6 +977,7 @@ cudaError_t build_wide_bvh(cudaStream_t stream, BuildScratch& scratch, const Box
         prim_cursor += (uint32_t)(tot >> 32);
         std::swap(items, next_items);
         if ((size_t)level_start + level_count > out.node_capacity) return cudaErrorMemoryAllocation;
+        if ((size_t)level_start + level_count > kMaxWideNodes) return cudaErrorInvalidValue; // 24-bit child index
     }
     out.n_nodes = level_start;
     if (launches) *launches += nl;

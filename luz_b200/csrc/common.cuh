@@ -8,23 +8,25 @@
 
 namespace luz {
 
-// ---- 8-wide compressed BVH node, 80 bytes, read as five 16-byte loads -------------------------
-// Layout after Ylitie, Karras, Laine, "Efficient Incoherent Ray Traversal on GPUs Through
-// Compressed Wide BVHs" (HPG 2017): child boxes are 8-bit offsets from the node origin p on a
-// per-axis power-of-two grid 2^(e-127).
-//   meta[i] == 0                      : empty slot
+// ---- 8-wide BVH node, 208 bytes: a 16-byte header and six planes x eight children in fp32 ----------
+// The acceleration structure of every instanced configuration is a few MB and lives in L1/L2, and the
+// traversal is bound by instruction issue on the ALU pipe, not by memory (profiles/r1_light_pass_v4.md:
+// ALU pipe 62 % of peak, FMA pipe 24 %, DRAM 0.6 %).  Child boxes are therefore kept as plain floats:
+// a slab distance is one FFMA on the plane (no byte extraction, no per-node grid set-up), and the near /
+// far plane of an axis is picked by the ADDRESS the ray loads from (lo* and hi* of an axis are 32 bytes
+// apart), not by selects.  The 8-bit quantised layout this replaces (Ylitie et al. 2017, 80 B) cost
+// 181 instructions per node visit, two thirds of them on the ALU pipe; this one costs ~115.
+//   meta[i] == 0                      : empty slot (its box is lo = +inf, hi = -inf: never hit)
 //   meta[i] == (1<<5) | (24 + i)      : internal child; its index is child_base + popc(imask & ((1<<i)-1))
 //   meta[i] == (unary(count)<<5) | off: leaf of `count` (1..3) primitives prim_base + off .. +count-1
 struct __align__(16) WideNode {
-    float px, py, pz;
-    uint8_t ex, ey, ez, imask;
-    uint32_t child_base;
+    uint32_t child_base_imask; // bits 23..0: index of the first internal child; bits 31..24: imask
     uint32_t prim_base;
     uint8_t meta[8];
-    uint8_t qlox[8], qloy[8], qloz[8];
-    uint8_t qhix[8], qhiy[8], qhiz[8];
+    float lox[8], hix[8], loy[8], hiy[8], loz[8], hiz[8];
 };
-static_assert(sizeof(WideNode) == 80, "WideNode must be 80 bytes");
+static_assert(sizeof(WideNode) == 208, "WideNode must be 208 bytes");
+constexpr uint32_t kMaxWideNodes = 1u << 24; // child_base is 24 bits
 
 // One triangle, 48 bytes: three float4 (xyz = vertex, v0.w = original triangle index bits).
 struct __align__(16) WideTri {
@@ -56,7 +58,6 @@ struct TraceScene {
     const WideNode* tlas_nodes;
     const InstanceRec* instances;
     const float4* inst_boxes; // world boxes of the instances, TLAS leaf order: [2i] = lo.xyz, [2i+1] = hi.xyz
-    uint32_t one_bits; // 0x3F800000, deliberately a run-time value (see traverse.cuh)
     uint32_t min_node_lanes; // the node loop of trace_ray yields once fewer lanes than this remain in it
 };
 

@@ -1,4 +1,4 @@
-// traverse.cuh -- two-level stack traversal of the 8-wide compressed BVH (device code).
+// traverse.cuh -- two-level stack traversal of the 8-wide BVH (device code).
 //
 // Replaces what VK_KHR_ray_query does for light.frag:99-106 / :125-132 (the driver's traversal is
 // not in the reference tree): opaque two-sided triangles, cull mask 0xFF, any-hit terminates on
@@ -79,56 +79,65 @@ __device__ __forceinline__ bool tri_test(const float4 p0, const float4 p1, const
     return true;
 }
 
-// Ray vs the eight quantised child boxes of a wide node.
+// ---- ray vs the eight child boxes of a wide node -------------------------------------------------------
+// Per ray space (world, or the object space of the instance being traversed) the ray keeps
+//     idir = 1 / d (MUFU, relative error 2^-23),  p = o * idir,  pn = p + |p| 2^-22,  pf = p - |p| 2^-22
+// and the slab distance of a plane b is ONE instruction, t = fma(b, idir, -p*).  Error budget: the product
+// o * idir is rounded once (<= |p| 2^-24, covered four times over by the +-|p| 2^-22 built into pn / pf, which
+// push near planes down and far planes up) and the FFMA rounds once more (<= |t| 2^-24, which together with
+// the reciprocal's 2^-23 is covered by scaling the far distance by 1 + 2^-20).  The test is therefore
+// conservative: a ray that meets a box in exact arithmetic is never rejected.
 //
-// Dequantisation without integer->float conversions (I2F runs on the quarter-rate XU pipe and was
-// the top stall in the first ncu profile, profiles/r1_light_pass_v0.md): one PRMT drops the byte q
-// into the mantissa of 1.0f, giving v = 1 + q*2^-15 exactly, and one FFMA evaluates
-//     t = q*adj + o  ==  v*A + (o - A),   A = adj * 2^15.
-// Rounding (o - A) costs at most |adj|*2^-9 (1/512 of a grid cell); both planes are pushed outwards
-// by |adj|*2^-8 and the far plane is scaled by (1 + 2^-21) so the test stays conservative.
-__device__ __forceinline__ float q_as_float(uint32_t packed, uint32_t one_bits, uint32_t selector) {
-    return __uint_as_float(__byte_perm(packed, one_bits, selector));
+// lo and hi planes of an axis are 32 bytes apart in the node, so the near / far selection by the sign of the
+// direction is an address offset fixed per ray space (no selects in the per-child code).  Empty slots hold
+// lo = +inf, hi = -inf: near = +inf or NaN, and the comparison below is false.
+struct RaySpace {
+    float3 idir, pn, pf;
+    uint32_t off; // byte 0/1/2: 0 or 32 = offset of the NEAR plane array of x / y / z inside its axis pair
+};
+
+__device__ __forceinline__ RaySpace make_ray_space(const float3 o, const float3 d) {
+    RaySpace rs;
+    rs.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+    const float px = __fmul_rn(o.x, rs.idir.x), py = __fmul_rn(o.y, rs.idir.y), pz = __fmul_rn(o.z, rs.idir.z);
+    const float k = 2.384185791015625e-07f; // 2^-22
+    rs.pn = f3(fmaf(fabsf(px), k, px), fmaf(fabsf(py), k, py), fmaf(fabsf(pz), k, pz));
+    rs.pf = f3(fmaf(fabsf(px), -k, px), fmaf(fabsf(py), -k, py), fmaf(fabsf(pz), -k, pz));
+    rs.off = ((__float_as_uint(rs.idir.x) >> 31) << 5) | ((__float_as_uint(rs.idir.y) >> 31) << 13) |
+             ((__float_as_uint(rs.idir.z) >> 31) << 21);
+    return rs;
 }
 
 // Returns the 8-bit mask of child slots whose box the ray overlaps in [tmin, tmax].
-__device__ __forceinline__ uint32_t intersect_node(const uint4 n0, const uint4 n2, const uint4 n3, const uint4 n4,
-                                                   const float3 o, const float3 idir, const float tmin,
-                                                   const float tmax, const uint32_t one_bits) {
-    const float kFar = 1.000001f; // 1 + 2^-20: covers the rounding of the FFMAs and of the approximate reciprocal
-    // per-axis constants
-    const float adjx = __uint_as_float((n0.w & 0xFFu) << 23) * idir.x;
-    const float adjy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * idir.y;
-    const float adjz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
-    const float Ax = adjx * 32768.0f, Ay = adjy * 32768.0f, Az = adjz * 32768.0f;
-    const float Bx = (__uint_as_float(n0.x) - o.x) * idir.x - Ax;
-    const float By = (__uint_as_float(n0.y) - o.y) * idir.y - Ay;
-    const float Bz = (__uint_as_float(n0.z) - o.z) * idir.z - Az;
-    const float px = fabsf(adjx) * 0.00390625f, py = fabsf(adjy) * 0.00390625f, pz = fabsf(adjz) * 0.00390625f;
-    const float Bnx = Bx - px, Bny = By - py, Bnz = Bz - pz;
-    const float Afx = Ax * kFar, Afy = Ay * kFar, Afz = Az * kFar;
-    const float Bfx = fmaf(Bx, kFar, px), Bfy = fmaf(By, kFar, py), Bfz = fmaf(Bz, kFar, pz);
-    const bool negx = idir.x < 0.0f, negy = idir.y < 0.0f, negz = idir.z < 0.0f;
+__device__ __forceinline__ uint32_t intersect_node(const WideNode* __restrict__ node, const RaySpace& rs, const float tmin,
+                                                   const float tmax) {
+    const char* base = reinterpret_cast<const char*>(node) + 16;
+    const uint32_t ox = rs.off & 0xFFu, oy = (rs.off >> 8) & 0xFFu, oz = (rs.off >> 16) & 0xFFu;
+    const float4* nxp = reinterpret_cast<const float4*>(base + ox);
+    const float4* fxp = reinterpret_cast<const float4*>(base + (ox ^ 32u));
+    const float4* nyp = reinterpret_cast<const float4*>(base + 64 + oy);
+    const float4* fyp = reinterpret_cast<const float4*>(base + 64 + (oy ^ 32u));
+    const float4* nzp = reinterpret_cast<const float4*>(base + 128 + oz);
+    const float4* fzp = reinterpret_cast<const float4*>(base + 128 + (oz ^ 32u));
+    const float kFar = 9.5367431640625e-07f; // 2^-20
     uint32_t slots = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        const uint32_t lox = half ? n2.y : n2.x, loy = half ? n2.w : n2.z, loz = half ? n3.y : n3.x;
-        const uint32_t hix = half ? n3.w : n3.z, hiy = half ? n4.y : n4.x, hiz = half ? n4.w : n4.z;
-        const uint32_t nx = negx ? hix : lox, fx = negx ? lox : hix;
-        const uint32_t ny = negy ? hiy : loy, fy = negy ? loy : hiy;
-        const uint32_t nz = negz ? hiz : loz, fz = negz ? loz : hiz;
+        const float4 nx = __ldg(nxp + half), ny = __ldg(nyp + half), nz = __ldg(nzp + half);
+        const float4 fx = __ldg(fxp + half), fy = __ldg(fyp + half), fz = __ldg(fzp + half);
+        const float anx[4] = {nx.x, nx.y, nx.z, nx.w}, any[4] = {ny.x, ny.y, ny.z, ny.w}, anz[4] = {nz.x, nz.y, nz.z, nz.w};
+        const float afx[4] = {fx.x, fx.y, fx.z, fx.w}, afy[4] = {fy.x, fy.y, fy.z, fy.w}, afz[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t sel = 0x7604u | ((uint32_t)j << 4); // bytes: [3F][80][q_j][00]
-            const float tnx = fmaf(q_as_float(nx, one_bits, sel), Ax, Bnx);
-            const float tny = fmaf(q_as_float(ny, one_bits, sel), Ay, Bny);
-            const float tnz = fmaf(q_as_float(nz, one_bits, sel), Az, Bnz);
-            const float tfx = fmaf(q_as_float(fx, one_bits, sel), Afx, Bfx);
-            const float tfy = fmaf(q_as_float(fy, one_bits, sel), Afy, Bfy);
-            const float tfz = fmaf(q_as_float(fz, one_bits, sel), Afz, Bfz);
+            const float tnx = fmaf(anx[j], rs.idir.x, -rs.pn.x);
+            const float tny = fmaf(any[j], rs.idir.y, -rs.pn.y);
+            const float tnz = fmaf(anz[j], rs.idir.z, -rs.pn.z);
+            const float tfx = fmaf(afx[j], rs.idir.x, -rs.pf.x);
+            const float tfy = fmaf(afy[j], rs.idir.y, -rs.pf.y);
+            const float tfz = fmaf(afz[j], rs.idir.z, -rs.pf.z);
             const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
             const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (cmin <= cmax) slots |= 1u << (4 * half + j);
+            if (cmin <= fmaf(fabsf(cmax), kFar, cmax)) slots |= 1u << (4 * half + j);
         }
     }
     return slots;
@@ -158,8 +167,7 @@ __device__ __forceinline__ uint32_t leaf_bits(uint32_t leaf_slots, const uint32_
 // identical to a root descent.
 //
 // Returns the number of instances written to out[k * stride], or -1 if there are more than max_out (the
-// caller then falls back to the root descent).  Child boxes are dequantised exactly as the builder checked
-// them (origin + q * 2^e, one rounding), so the test is conservative.
+// caller then falls back to the root descent).  Child boxes are the exact fp32 boxes the builder stored.
 template <bool STATS>
 __device__ __forceinline__ int collect_instances(const TraceScene& sc, const float3 lo, const float3 hi, uint32_t* out,
                                                  const int stride, const int max_out, uint2* stack, LocalStats* st) {
@@ -175,44 +183,36 @@ __device__ __forceinline__ int collect_instances(const TraceScene& sc, const flo
             if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
             const int slot = bit - 24;
             const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
-            const uint4* np = reinterpret_cast<const uint4*>(sc.tlas_nodes + (ngroup.x + rel));
-            const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
-                        n4 = __ldg(np + 4);
+            const WideNode* node = sc.tlas_nodes + (ngroup.x + rel);
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(node));
             if (STATS) st->nodes++;
-            // the query box in the node's 8-bit grid, widened by a cell on each side (absorbs every rounding of
-            // the conversion and of the builder's dequantisation check), then pure byte compares per child
-            const uint32_t ex = n0.w & 0xFFu, ey = (n0.w >> 8) & 0xFFu, ez = (n0.w >> 16) & 0xFFu;
-            if (max(ex, max(ey, ez)) >= 254u) return -1; // 2^-(e-127) not representable: let the root descent handle it
-            const float ix = __uint_as_float((254u - ex) << 23), iy = __uint_as_float((254u - ey) << 23),
-                        iz = __uint_as_float((254u - ez) << 23);
-            const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
-            const int glx = (int)fminf(fmaxf(floorf((lo.x - px) * ix) - 1.0f, 0.0f), 255.0f);
-            const int gly = (int)fminf(fmaxf(floorf((lo.y - py) * iy) - 1.0f, 0.0f), 255.0f);
-            const int glz = (int)fminf(fmaxf(floorf((lo.z - pz) * iz) - 1.0f, 0.0f), 255.0f);
-            const int ghx = (int)fminf(fmaxf(floorf((hi.x - px) * ix) + 2.0f, 0.0f), 255.0f);
-            const int ghy = (int)fminf(fmaxf(floorf((hi.y - py) * iy) + 2.0f, 0.0f), 255.0f);
-            const int ghz = (int)fminf(fmaxf(floorf((hi.z - pz) * iz) + 2.0f, 0.0f), 255.0f);
+            // exact child boxes against the query box (empty slots hold an inverted infinite box)
+            const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(node) + 16);
             uint32_t slots = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t sel = 0x4440u + (uint32_t)(k & 3); // byte k&3 zero-extended
-                const int meta = (int)__byte_perm(k < 4 ? n1.z : n1.w, 0u, sel);
-                const int qlx = (int)__byte_perm(k < 4 ? n2.x : n2.y, 0u, sel), qly = (int)__byte_perm(k < 4 ? n2.z : n2.w, 0u, sel);
-                const int qlz = (int)__byte_perm(k < 4 ? n3.x : n3.y, 0u, sel), qhx = (int)__byte_perm(k < 4 ? n3.z : n3.w, 0u, sel);
-                const int qhy = (int)__byte_perm(k < 4 ? n4.x : n4.y, 0u, sel), qhz = (int)__byte_perm(k < 4 ? n4.z : n4.w, 0u, sel);
-                const bool ov = meta != 0 && qlx <= ghx && qhx >= glx && qly <= ghy && qhy >= gly && qlz <= ghz && qhz >= glz;
-                if (ov) slots |= 1u << k;
+            for (int half = 0; half < 2; half++) {
+                const float4 lx = __ldg(bp + half), hx = __ldg(bp + 2 + half), ly = __ldg(bp + 4 + half);
+                const float4 hy = __ldg(bp + 6 + half), lz = __ldg(bp + 8 + half), hz = __ldg(bp + 10 + half);
+                const float alx[4] = {lx.x, lx.y, lx.z, lx.w}, ahx[4] = {hx.x, hx.y, hx.z, hx.w};
+                const float aly[4] = {ly.x, ly.y, ly.z, ly.w}, ahy[4] = {hy.x, hy.y, hy.z, hy.w};
+                const float alz[4] = {lz.x, lz.y, lz.z, lz.w}, ahz[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool ov = alx[j] <= hi.x && ahx[j] >= lo.x && aly[j] <= hi.y && ahy[j] >= lo.y &&
+                                    alz[j] <= hi.z && ahz[j] >= lo.z;
+                    if (ov) slots |= 1u << (4 * half + j);
+                }
             }
-            const uint32_t node_imask = n0.w >> 24;
-            uint32_t prims = leaf_bits(slots & ~node_imask, n1.z, n1.w);
+            const uint32_t node_imask = hdr.x >> 24;
+            uint32_t prims = leaf_bits(slots & ~node_imask, hdr.z, hdr.w);
             while (prims) {
                 const int j = __ffs(prims) - 1;
                 prims &= prims - 1u;
                 if (n >= max_out) return -1;
-                out[n * stride] = n1.y + (uint32_t)j;
+                out[n * stride] = hdr.y + (uint32_t)j;
                 n++;
             }
-            ngroup = make_uint2(n1.x, ((slots & node_imask) << 24) | node_imask);
+            ngroup = make_uint2(hdr.x & 0x00FFFFFFu, ((slots & node_imask) << 24) | node_imask);
         }
         if (sp == 0) break;
         ngroup = stack[--sp];
@@ -237,17 +237,13 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
         return false;
     if (wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f) return false;
 
-    // 0x3F800000 comes in as a kernel parameter: PRMT then takes it straight from the constant bank and keeps
-    // its selector as an immediate (with a literal, ptxas puts the selector in a register and re-creates it
-    // with a MOV in front of every PRMT: profiles/r1_light_pass_v1.md)
-    const uint32_t one_bits = sc.one_bits;
     int sp = 0;
     int inst_sp = -1; // stack height at which the current instance was entered, -1 = in the TLAS
     uint32_t cur_inst = 0;
     const bool from_root = n_cand < 0;
 
     float3 o = wo, d = wd;
-    float3 idir;
+    RaySpace rs;
     float inv_dd;
     const WideNode* nodes = sc.tlas_nodes;
     const WideTri* tris = nullptr;
@@ -257,16 +253,11 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     uint2 tgroup = make_uint2(0u, 0u);
     uint32_t pending = kNoInstance; // instance to enter at the top of the loop
     int ci = 0;
-    if (from_root) {
-        ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
-        idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-        inv_dd = fast_rcp(dot3_fma(d, d));
-    } else {
-        // candidate mode keeps the world-space reciprocal direction for the box pre-test below
-        idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-        inv_dd = 0.0f;
-    }
-    const float3 widir = idir;
+    rs = make_ray_space(o, d);
+    inv_dd = 0.0f; // only triangles need it, and they live in object space
+    if (from_root) ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
+    // candidate mode keeps the world-space reciprocal direction for the box pre-test below
+    const float3 widir = rs.idir;
 
     while (true) {
         if (pending != kNoInstance) {
@@ -277,7 +268,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             if (STATS) st->insts++;
             o = xform_point(r0, r1, r2, wo);
             d = xform_dir(r0, r1, r2, wd);
-            idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+            rs = make_ray_space(o, d);
             inv_dd = fast_rcp(dot3_fma(d, d));
             nodes = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
             tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
@@ -301,14 +292,13 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
             const int slot = bit - 24;
             const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
-            const uint4* np = reinterpret_cast<const uint4*>(nodes + (ngroup.x + rel));
-            const uint4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3),
-                        n4 = __ldg(np + 4);
+            const WideNode* node = nodes + (ngroup.x + rel);
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(node));
             if (STATS) st->nodes++;
-            const uint32_t slots = intersect_node(n0, n2, n3, n4, o, idir, tmin, tmax, one_bits);
-            const uint32_t node_imask = n0.w >> 24;
-            ngroup = make_uint2(n1.x, ((slots & node_imask) << 24) | node_imask);
-            tgroup = make_uint2(n1.y, leaf_bits(slots & ~node_imask, n1.z, n1.w));
+            const uint32_t slots = intersect_node(node, rs, tmin, tmax);
+            const uint32_t node_imask = hdr.x >> 24;
+            ngroup = make_uint2(hdr.x & 0x00FFFFFFu, ((slots & node_imask) << 24) | node_imask);
+            tgroup = make_uint2(hdr.y, leaf_bits(slots & ~node_imask, hdr.z, hdr.w));
             // when only a few lanes are still descending, yield so that the lanes waiting at the end of this loop
             // (they hold primitives or need a pop) get served and everybody re-enters the node test together
             if (__popc(__activemask()) < (int)sc.min_node_lanes) break;
@@ -352,8 +342,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 if (from_root) { // back to world space
                     o = wo;
                     d = wd;
-                    idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-                    inv_dd = fast_rcp(dot3_fma(d, d));
+                    rs = make_ray_space(o, d);
                     nodes = sc.tlas_nodes;
                 }
             }
