@@ -183,7 +183,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
             }
             // ---- the rays of this source ----
             float hits = 0.0f;
-            for (int i = 0; i < n_samples; i++) {
+            int n_trace = n_samples;
+            if (n_cand == 0) { // no instance within reach of any AO ray of this pixel: every one of them misses
+                n_rays += counted * (uint32_t)max(n_samples, 0);
+                n_trace = 0;
+            }
+            for (int i = 0; i < n_trace; i++) {
                 const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
                 float sn, cs;
                 float3 dir;

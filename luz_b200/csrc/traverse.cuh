@@ -81,18 +81,21 @@ __device__ __forceinline__ bool tri_test(const float4 p0, const float4 p1, const
 
 // ---- ray vs the eight child boxes of a wide node -------------------------------------------------------
 // Per ray space (world, or the object space of the instance being traversed) the ray keeps
-//     idir = 1 / d (MUFU, relative error 2^-23),  p = o * idir,  pn = p + |p| 2^-22,  pf = p - |p| 2^-22
-// and the slab distance of a plane b is ONE instruction, t = fma(b, idir, -p*).  Error budget: the product
-// o * idir is rounded once (<= |p| 2^-24, covered four times over by the +-|p| 2^-22 built into pn / pf, which
-// push near planes down and far planes up) and the FFMA rounds once more (<= |t| 2^-24, which together with
-// the reciprocal's 2^-23 is covered by scaling the far distance by 1 + 2^-20).  The test is therefore
-// conservative: a ray that meets a box in exact arithmetic is never rejected.
+//     idir = 1 / d (MUFU, relative error 2^-23),  p = o * idir,  npn = -(p + |p| 2^-22),  npf = -(p - |p| 2^-22)
+// and the slab distance of a plane b is half an instruction: t = fma(b, idir, np*) is issued as the packed
+// FFMA2 of sm_100 (fma.rn.f32x2: two IEEE fp32 FMAs per issue slot, the ray constants broadcast from one
+// register, the plane pair exactly as LDG.128 delivered it), because this kernel is bound by instruction issue,
+// not by the FMA pipe.  Error budget: the product o * idir is rounded once (<= |p| 2^-24, covered four times over
+// by the +-|p| 2^-22 built into npn / npf, which push near planes down and far planes up) and the FMA rounds once
+// more (<= |t| 2^-24, which together with the reciprocal's 2^-23 is covered by scaling the far distance by
+// 1 + 2^-20, one packed FMUL2 per child pair).  The test is therefore conservative for rays with tmin >= 0 (what
+// VK_KHR_ray_query requires of its callers): a ray that meets a box in exact arithmetic is never rejected.
 //
 // lo and hi planes of an axis are 32 bytes apart in the node, so the near / far selection by the sign of the
 // direction is an address offset fixed per ray space (no selects in the per-child code).  Empty slots hold
 // lo = +inf, hi = -inf: near = +inf or NaN, and the comparison below is false.
 struct RaySpace {
-    float3 idir, pn, pf;
+    float3 idir, npn, npf;
     uint32_t off; // byte 0/1/2: 0 or 32 = offset of the NEAR plane array of x / y / z inside its axis pair
 };
 
@@ -101,11 +104,32 @@ __device__ __forceinline__ RaySpace make_ray_space(const float3 o, const float3 
     rs.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
     const float px = __fmul_rn(o.x, rs.idir.x), py = __fmul_rn(o.y, rs.idir.y), pz = __fmul_rn(o.z, rs.idir.z);
     const float k = 2.384185791015625e-07f; // 2^-22
-    rs.pn = f3(fmaf(fabsf(px), k, px), fmaf(fabsf(py), k, py), fmaf(fabsf(pz), k, pz));
-    rs.pf = f3(fmaf(fabsf(px), -k, px), fmaf(fabsf(py), -k, py), fmaf(fabsf(pz), -k, pz));
+    rs.npn = f3(-fmaf(fabsf(px), k, px), -fmaf(fabsf(py), k, py), -fmaf(fabsf(pz), k, pz));
+    rs.npf = f3(-fmaf(fabsf(px), -k, px), -fmaf(fabsf(py), -k, py), -fmaf(fabsf(pz), -k, pz));
     rs.off = ((__float_as_uint(rs.idir.x) >> 31) << 5) | ((__float_as_uint(rs.idir.y) >> 31) << 13) |
              ((__float_as_uint(rs.idir.z) >> 31) << 21);
     return rs;
+}
+
+// (a0, a1) * b + c and (a0, a1) * b as one packed instruction each; bitwise equal to two fmaf() / __fmul_rn().
+__device__ __forceinline__ float2 fma2_bcast(const float a0, const float a1, const float b, const float c) {
+    unsigned long long A, B, C, D;
+    float2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(D));
+    return r;
+}
+__device__ __forceinline__ float2 mul2_bcast(const float a0, const float a1, const float b) {
+    unsigned long long A, B, D;
+    float2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(D));
+    return r;
 }
 
 // Returns the 8-bit mask of child slots whose box the ray overlaps in [tmin, tmax].
@@ -119,7 +143,7 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode* __restrict__ 
     const float4* fyp = reinterpret_cast<const float4*>(base + 64 + (oy ^ 32u));
     const float4* nzp = reinterpret_cast<const float4*>(base + 128 + oz);
     const float4* fzp = reinterpret_cast<const float4*>(base + 128 + (oz ^ 32u));
-    const float kFar = 9.5367431640625e-07f; // 2^-20
+    const float kFar = 1.00000095367431640625f; // 1 + 2^-20
     uint32_t slots = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
@@ -128,16 +152,20 @@ __device__ __forceinline__ uint32_t intersect_node(const WideNode* __restrict__ 
         const float anx[4] = {nx.x, nx.y, nx.z, nx.w}, any[4] = {ny.x, ny.y, ny.z, ny.w}, anz[4] = {nz.x, nz.y, nz.z, nz.w};
         const float afx[4] = {fx.x, fx.y, fx.z, fx.w}, afy[4] = {fy.x, fy.y, fy.z, fy.w}, afz[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float tnx = fmaf(anx[j], rs.idir.x, -rs.pn.x);
-            const float tny = fmaf(any[j], rs.idir.y, -rs.pn.y);
-            const float tnz = fmaf(anz[j], rs.idir.z, -rs.pn.z);
-            const float tfx = fmaf(afx[j], rs.idir.x, -rs.pf.x);
-            const float tfy = fmaf(afy[j], rs.idir.y, -rs.pf.y);
-            const float tfz = fmaf(afz[j], rs.idir.z, -rs.pf.z);
-            const float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (cmin <= fmaf(fabsf(cmax), kFar, cmax)) slots |= 1u << (4 * half + j);
+        for (int j = 0; j < 4; j += 2) {
+            const float2 tnx = fma2_bcast(anx[j], anx[j + 1], rs.idir.x, rs.npn.x);
+            const float2 tny = fma2_bcast(any[j], any[j + 1], rs.idir.y, rs.npn.y);
+            const float2 tnz = fma2_bcast(anz[j], anz[j + 1], rs.idir.z, rs.npn.z);
+            const float2 tfx = fma2_bcast(afx[j], afx[j + 1], rs.idir.x, rs.npf.x);
+            const float2 tfy = fma2_bcast(afy[j], afy[j + 1], rs.idir.y, rs.npf.y);
+            const float2 tfz = fma2_bcast(afz[j], afz[j + 1], rs.idir.z, rs.npf.z);
+            const float cmin0 = fmaxf(fmaxf(tnx.x, tny.x), fmaxf(tnz.x, tmin));
+            const float cmin1 = fmaxf(fmaxf(tnx.y, tny.y), fmaxf(tnz.y, tmin));
+            const float cmax0 = fminf(fminf(tfx.x, tfy.x), fminf(tfz.x, tmax));
+            const float cmax1 = fminf(fminf(tfx.y, tfy.y), fminf(tfz.y, tmax));
+            const float2 cfar = mul2_bcast(cmax0, cmax1, kFar);
+            if (cmin0 <= cfar.x) slots |= 1u << (4 * half + j);
+            if (cmin1 <= cfar.y) slots |= 1u << (4 * half + j + 1);
         }
     }
     return slots;
