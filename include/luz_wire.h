@@ -31,6 +31,10 @@ extern "C" {
 #define LUZW_SHADOW_RAYTRACING 1 /* LuzCommon.h:28 */
 #define LUZW_SHADOW_MAP 2        /* LuzCommon.h:29 */
 
+#define LUZW_VOLUMETRIC_DISABLED 0     /* AssetManager.hpp:194 */
+#define LUZW_VOLUMETRIC_SCREEN_SPACE 1 /* LuzCommon.h:31 */
+#define LUZW_VOLUMETRIC_SHADOW_MAP 2   /* LuzCommon.h:32 */
+
 typedef struct luzw_light_block { /* 480 B */
     float color[3];
     float intensity;

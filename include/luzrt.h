@@ -102,6 +102,7 @@ typedef struct luzrt_timings {
     float taa_ms;     /* last luzrt_taa_pass       ("TAAPass", main.cpp:281)                 */
     float gather_ms;  /* last luzrt_gather                                                    */
     float compose_ms; /* last luzrt_compose_pass   ("ComposePass", main.cpp:293)             */
+    float volumetric_ms; /* last luzrt_volumetric_pass ("VolumetricLightPass", main.cpp:274)    */
 } luzrt_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -192,6 +193,17 @@ LUZRT_API int luzrt_set_debug(luzrt_ctx* ctx, uint32_t flags);
  * (DeferredRenderer.cpp:324-345, light.frag:171-235): writes lightA for this rank's rows
  * (plus the rows TAA's 3x3 taps need). */
 LUZRT_API int luzrt_light_pass(luzrt_ctx* ctx, uint32_t frame);
+
+/* == the block `if (gpuScene.AnyVolumetricLight())` of RenderFrame
+ * (main.cpp:274-279), i.e. DeferredRenderer::ScreenSpaceVolumetricLightPass(gpuScene, frame)
+ * (DeferredRenderer.cpp:294-307, screenSpaceVolumetricLight.comp:22-62): adds the screen-space
+ * light shafts of every light with volumetricType == 1 into lightA, after luzrt_light_pass and
+ * before luzrt_taa_pass.  A no-op when the scene block has no such light (== AnyVolumetricLight()
+ * false).  The march reads depth anywhere in the frame: with world > 1, luzrt_set_gbuffer /
+ * luzrt_prefetch_gbuffer / luzrt_gbuffer_pass fill the whole depth plane on every rank while the
+ * scene block set by luzrt_set_scene has such a light.  Lights with volumetricType == 2
+ * (shadow-map volumetrics, shadowMapVolumetricLight.comp) are rejected with LUZRT_E_INVALID. */
+LUZRT_API int luzrt_volumetric_pass(luzrt_ctx* ctx, uint32_t frame);
 
 /* == DeferredRenderer::TAAPass with scene->taaEnabled (DeferredRenderer.cpp:425-445,
  * taa.comp:271-308) including its swap(lightA, lightB).  Not calling it == taaEnabled false. */

@@ -59,7 +59,7 @@ struct Texture {
     uint2 size{0, 0};
 };
 
-enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_COUNT };
+enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_VOLUMETRIC, EV_COUNT };
 
 } // namespace
 
@@ -94,6 +94,11 @@ struct luzrt_ctx {
     LightRec* d_lights = nullptr;
     size_t lights_cap = 0;
     uint32_t rays_per_lit_pixel = 0, shadow_bits = 0;
+    VolLight* d_vol_lights = nullptr; // lights with a volumetric type, scene order
+    size_t vol_lights_cap = 0;
+    int n_vol_lights = 0;
+    bool need_full_depth = false; // screen-space volumetrics read depth anywhere in the frame
+    bool has_shadow_map_volumetric = false;
 
     std::vector<Blas> blas;
     BuildScratch scratch;
@@ -334,7 +339,7 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < EV_COUNT; i++)
@@ -651,6 +656,7 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
     DeviceGuard g(c->device);
     const int n = s->num_lights + (int)n_extra;
     std::vector<LightRec> recs((size_t)std::max(n, 1));
+    std::vector<VolLight> vols;
     uint32_t shadow_bits = 0;
     for (int i = 0; i < n; i++) {
         const luzw_light_block& l = i < LUZW_MAX_LIGHTS ? s->lights[i] : extra[i - LUZW_MAX_LIGHTS];
@@ -665,8 +671,30 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
         r.radius = l.radius;
         r.shadow_map = l.shadow_map;
         if (s->shadow_type == LUZW_SHADOW_RAYTRACING && l.num_shadow_samples > 0) shadow_bits += (uint32_t)l.num_shadow_samples;
+        if (l.volumetric_type == LUZW_VOLUMETRIC_SCREEN_SPACE || l.volumetric_type == LUZW_VOLUMETRIC_SHADOW_MAP) {
+            VolLight v{};
+            v.color_intensity = r.color_intensity;
+            v.position_type = make_float4(l.position[0], l.position[1], l.position[2], 0.0f);
+            memcpy(&v.position_type.w, &l.type, 4);
+            v.direction_absorption = make_float4(l.direction[0], l.direction[1], l.direction[2], l.volumetric_absorption);
+            v.samples = l.volumetric_samples;
+            v.volumetric_type = l.volumetric_type;
+            v.light_index = i;
+            vols.push_back(v);
+        }
     }
     int rc;
+    c->n_vol_lights = (int)vols.size();
+    c->need_full_depth = false;
+    c->has_shadow_map_volumetric = false;
+    for (const VolLight& v : vols) {
+        if (v.volumetric_type == LUZW_VOLUMETRIC_SCREEN_SPACE) c->need_full_depth = true;
+        if (v.volumetric_type == LUZW_VOLUMETRIC_SHADOW_MAP) c->has_shadow_map_volumetric = true;
+    }
+    if (!vols.empty()) {
+        if ((rc = grow(c, c->d_vol_lights, c->vol_lights_cap, vols.size())) != LUZRT_OK) return rc;
+        CU(c, cudaMemcpyAsync(c->d_vol_lights, vols.data(), vols.size() * sizeof(VolLight), cudaMemcpyHostToDevice, c->stream));
+    }
     if ((rc = grow(c, c->d_lights, c->lights_cap, recs.size())) != LUZRT_OK) return rc;
     CU(c, cudaMemcpyAsync(c->d_lights, recs.data(), recs.size() * sizeof(LightRec), cudaMemcpyHostToDevice, c->stream));
     FrameConst& fc = c->fc;
@@ -708,6 +736,10 @@ int copy_gbuffer(luzrt_ctx* c, const GbufPlanes& dst, const void* const src[5], 
     for (int pl = 0; pl < 5; pl++) {
         if (!src[pl]) continue;
         const size_t row = (size_t)c->w * bpp[pl];
+        if (pl == 4 && c->need_full_depth && c->world > 1) { // the volumetric march reads depth anywhere in the frame
+            CU(c, cudaMemcpyAsync(dst.p[pl], src[pl], (size_t)c->h * row, kind, stream));
+            continue;
+        }
         // bands that lie fully inside the image repeat at a fixed pitch: one strided copy covers them all
         size_t first_regular = seg.size(), n_regular = 0;
         for (size_t s2 = 0; s2 < seg.size(); s2++) {
@@ -883,7 +915,8 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     a.material = c->material;
     a.emission = c->emission;
     a.depth = c->depth;
-    a.rows = shade_bands(c);
+    // screen-space volumetrics read depth anywhere in the frame: every rank then renders all rows
+    a.rows = (c->need_full_depth && c->world > 1) ? BandSet{0, c->h, c->h, 1} : shade_bands(c);
     ev_begin(c, EV_GBUF);
     CU(c, launch_gbuffer_pass(c->stream, a));
     c->launches++;
@@ -946,6 +979,34 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     CU(c, launch_light_pass(c->stream, a, masks, stats));
     c->launches++;
     ev_end(c, EV_LIGHT);
+    return LUZRT_OK;
+}
+
+int luzrt_volumetric_pass(luzrt_ctx* c, uint32_t frame) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
+    if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
+    if (c->n_vol_lights == 0) return LUZRT_OK; // AnyVolumetricLight() == false (main.cpp:275)
+    if (c->has_shadow_map_volumetric)
+        return fail(c, LUZRT_E_INVALID, "shadow-map volumetrics (volumetricType 2) are outside this path");
+    if (!c->blue_noise) return fail(c, LUZRT_E_STATE, "luzrt_set_blue_noise has not been called");
+    DeviceGuard g(c->device);
+    VolumetricArgs a{};
+    a.fc = c->fc;
+    a.fc.frame_mod = (int)((int32_t)frame % 128);
+    a.fc.bn_w = c->bn_w;
+    a.fc.bn_h = c->bn_h;
+    a.depth = c->depth;
+    a.blue_noise = c->blue_noise;
+    a.lights = c->d_vol_lights;
+    a.n_lights = c->n_vol_lights;
+    a.light = c->lightA;
+    a.rows = shade_bands(c);
+    CU(c, wait_gather(c, a.light));
+    ev_begin(c, EV_VOLUMETRIC);
+    CU(c, launch_volumetric_screen(c->stream, a));
+    c->launches++;
+    ev_end(c, EV_VOLUMETRIC);
     return LUZRT_OK;
 }
 
@@ -1046,7 +1107,7 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
         float ms[EV_COUNT] = {0};
         for (int i = 0; i < EV_COUNT; i++)
             if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], c->ev[i][0], c->ev[i][1]);
-        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE]};
+        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC]};
         memcpy(dst, &t, sizeof(t));
         return LUZRT_OK;
     }

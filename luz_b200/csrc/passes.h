@@ -57,6 +57,29 @@ struct GbufferArgs {
     BandSet rows;
 };
 
+// one light with a volumetric type (LightBlock fields the volumetric shaders read), scene order
+struct __align__(16) VolLight {
+    float4 color_intensity;
+    float4 position_type;        // w: light type (int bits)
+    float4 direction_absorption; // w: volumetricAbsorption
+    int samples;
+    int volumetric_type;
+    int light_index;
+    int pad;
+};
+static_assert(sizeof(VolLight) == 64, "VolLight");
+
+struct VolumetricArgs {
+    FrameConst fc; // frame_mod, bn_w, bn_h filled like the light pass
+    const float* depth;
+    const uchar4* blue_noise;
+    const VolLight* lights;
+    int n_lights;
+    float4* light; // lightA, read-modify-write
+    BandSet rows;  // the rows the light pass shaded (own bands + halo rows)
+};
+
+cudaError_t launch_volumetric_screen(cudaStream_t stream, const VolumetricArgs& args);
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats);
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
 cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,

@@ -104,6 +104,8 @@ LUZHOST_API int luzhost_render_frame(luzhost_app* a, uint32_t flags) {
     LightConstants lc;
     lc.frameID = a->frameCount;
     if ((rc = a->renderer->LightPass(lc)) != LUZRT_OK) return rtfail(a, rc);
+    if (a->gpuScene->AnyVolumetricLight()) // main.cpp:274-279
+        if ((rc = a->renderer->ScreenSpaceVolumetricLightPass(*a->gpuScene, a->frameCount)) != LUZRT_OK) return rtfail(a, rc);
     if ((rc = a->renderer->TAAPass(*a->gpuScene, a->scene)) != LUZRT_OK) return rtfail(a, rc);
     if (flags & LUZHOST_FRAME_COMPOSE)
         if ((rc = a->renderer->ComposePass(a->scene)) != LUZRT_OK) return rtfail(a, rc);

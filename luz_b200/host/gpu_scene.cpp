@@ -140,6 +140,7 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
         firstFrame = false;
     }
 
+    anyVolumetricLight = false; // GPUScene.cpp:237
     for (const auto& light : scene->GetAll<LightNode>(ObjectType::LightNode)) {
         luzw_light_block local{};
         luzw_light_block* block;
@@ -165,11 +166,13 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
         if (light->volumetricType == LightNode::ScreenSpace) {
             block->volumetric_samples = light->volumetricScreenSamples;
             block->volumetric_absorption = light->volumetricScreenAbsorption;
+            anyVolumetricLight = true;
         } else if (light->volumetricType == LightNode::ShadowMapVolumetric) {
             block->volumetric_weight = light->volumetricShadowWeight;
             block->volumetric_samples = light->volumetricShadowSamples;
             block->volumetric_density = light->volumetricShadowDensity;
             block->volumetric_absorption = light->volumetricShadowAbsorption;
+            anyVolumetricLight = true;
         }
     }
     put_vec3(s.ambient_light_color, scene->ambientLightColor);
@@ -201,6 +204,7 @@ int DeferredRenderer::OpaquePass(GPUScene& g) {
     return luzrt_gbuffer_pass(rt, g.modelsBlock.empty() ? nullptr : g.modelsBlock.data(), (uint32_t)g.modelsBlock.size());
 }
 int DeferredRenderer::LightPass(LightConstants c) { return luzrt_light_pass(rt, (uint32_t)c.frameID); }
+int DeferredRenderer::ScreenSpaceVolumetricLightPass(GPUScene&, int frame) { return luzrt_volumetric_pass(rt, (uint32_t)frame); }
 int DeferredRenderer::TAAPass(GPUScene&, const Ref<SceneAsset>& scene) {
     if (!scene->taaEnabled) return LUZRT_OK; // DeferredRenderer.cpp:426
     int rc = luzrt_taa_pass(rt, scene->taaReconstruct ? 1 : 0);

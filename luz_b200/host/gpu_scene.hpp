@@ -52,6 +52,8 @@ struct GPUScene {
     std::vector<luzrt_instance> instances;
     std::unordered_map<UUID, GPUMesh> meshes;
     std::unordered_map<UUID, GPUTexture> textures;
+    bool anyVolumetricLight = false; // GPUScene.cpp:16, :403-405
+    bool AnyVolumetricLight() const { return anyVolumetricLight; }
     bool firstFrame = true;
     int32_t nextCpuRid = 0;
 };
@@ -65,6 +67,7 @@ struct DeferredRenderer {
     int CreateImages(uint32_t width, uint32_t height);                      // DeferredRenderer.cpp:175-248
     int OpaquePass(GPUScene& gpuScene);                                     // main.cpp:242-258 (G-buffer)
     int LightPass(LightConstants constants);                                // DeferredRenderer.cpp:324-345
+    int ScreenSpaceVolumetricLightPass(GPUScene& gpuScene, int frame);      // :294-307
     int TAAPass(GPUScene& gpuScene, const Ref<SceneAsset>& scene);          // :425-445
     int ComposePass(const Ref<SceneAsset>& scene);                          // :347-370
     int SwapLightHistory();                                                 // :469-471

@@ -24,7 +24,7 @@ EXPORTS = [
     "luzrt_gather", "luzrt_compose_pass", "luzrt_swap_light_history", "luzrt_read", "luzrt_device_ptr",
     "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_bands", "luzrt_read_owned",
     "luzrt_prefetch_gbuffer", "luzrt_flip_gbuffer", "luzrt_read_owned_async", "luzrt_read_wait",
-    "luzrt_probe_read_bandwidth",
+    "luzrt_probe_read_bandwidth", "luzrt_volumetric_pass",
 ]
 
 
@@ -66,6 +66,7 @@ def load_library():
         "luzrt_set_debug": (i32, [vp, u32]),
         "luzrt_light_pass": (i32, [vp, u32]),
         "luzrt_taa_pass": (i32, [vp, i32]),
+        "luzrt_volumetric_pass": (i32, [vp, u32]),
         "luzrt_gather": (i32, [vp]),
         "luzrt_compose_pass": (i32, [vp, C.c_float]),
         "luzrt_swap_light_history": (i32, [vp]),
@@ -203,6 +204,9 @@ class LuzRT:
 
     def light_pass(self, frame):
         self._ck(self.lib.luzrt_light_pass(self.h, frame))
+
+    def volumetric_pass(self, frame):
+        self._ck(self.lib.luzrt_volumetric_pass(self.h, frame))
 
     def taa_pass(self, reconstruct=True):
         self._ck(self.lib.luzrt_taa_pass(self.h, 1 if reconstruct else 0))

@@ -969,6 +969,87 @@ int orc_taa_pass(const luzw_scene_block* scene, uint32_t width, uint32_t height,
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// screenSpaceVolumetricLight.comp:22-62, dispatched between the light
+// pass and TAA (main.cpp:274-279, DeferredRenderer.cpp:294-307) when any light has a volumetric
+// type.  Per pixel and per light with volumetricType == VOLUMETRIC_TYPE_SCREEN_SPACE the shader
+// marches `volumetricSamples` steps from the pixel towards the light's screen position and adds
+// light for every step that lands on background (depth == 1).  pixelUV = pixelPos / imageSize
+// (texel CORNER, :27); the depth fetches are texture() taps through the LINEAR / REPEAT sampler
+// at arbitrary uv, i.e. genuine bilinear fetches.  They are restated as nested lerps
+// a + w * (b - a), which return a constant neighbourhood exactly like the fixed-point weights
+// of a texture unit do, so that `== 1.0` (:50) means "all four texels are background".
+// ------------------------------------------------------------------------------------------
+namespace {
+inline float bilinear1(const float* d, int w, int h, float u, float v) {
+    const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int x0 = wrapi((int)fx0, w), y0 = wrapi((int)fy0, h);
+    const int x1 = wrapi((int)fx0 + 1, w), y1 = wrapi((int)fy0 + 1, h);
+    const float t00 = d[(size_t)y0 * w + x0], t10 = d[(size_t)y0 * w + x1];
+    const float t01 = d[(size_t)y1 * w + x0], t11 = d[(size_t)y1 * w + x1];
+    const float top = t00 + fx * (t10 - t00);
+    const float bot = t01 + fx * (t11 - t01);
+    return top + fy * (bot - top);
+}
+} // namespace
+
+int orc_volumetric_screen_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                               uint32_t width, uint32_t height, const float* depth, const uint8_t* bn, uint32_t bn_w,
+                               uint32_t bn_h, uint32_t frame, uint32_t y0, uint32_t y1, float* light_inout) {
+    const int n_lights = scene->num_lights + (int)n_extra;
+    const int frame_mod = (int)((int32_t)frame % 128);
+    const int W = (int)width, H = (int)height;
+#pragma omp parallel for schedule(dynamic, 4) num_threads(orc_get_threads())
+    for (int y = (int)y0; y < (int)y1; y++) {
+        for (int x = 0; x < W; x++) {
+            const float pu = (float)x / (float)W, pv = (float)y / (float)H; // :27
+            const uint8_t* t = bn + 4 * ((size_t)(y % (int)bn_h) * bn_w + (size_t)(x % (int)bn_w));
+            const float bn_r = (float)t[0] / 255.0f; // :16-20, .r only
+            V3 radiance = v3(0.0f, 0.0f, 0.0f);
+            for (int li = 0; li < n_lights; li++) {
+                const luzw_light_block& light = light_at(scene, extra_lights, li);
+                if (light.volumetric_type != 1) continue; // VOLUMETRIC_TYPE_SCREEN_SPACE, :32
+                const V3 lpos = v3(light.position[0], light.position[1], light.position[2]);
+                V4 lp = mul(scene->view_proj, V4{lpos.x, lpos.y, lpos.z, 1.0f});
+                if (light.type == 2) // LUZ_LIGHT_TYPE_DIRECTIONAL, :37-39
+                    lp = mul(scene->view_proj, V4{-light.direction[0] * 10000.0f, -light.direction[1] * 10000.0f,
+                                                  -light.direction[2] * 10000.0f, 1.0f});
+                const float lu = (lp.x / lp.w) * 0.5f + 0.5f, lv = (lp.y / lp.w) * 0.5f + 0.5f; // :41
+                const int samples = light.volumetric_samples;
+                const float absorption = light.volumetric_absorption / 1000.0f;
+                const float inv_n = 1.0f / (float)samples;
+                const float du = (pu - lu) * inv_n, dv = (pv - lv) * inv_n; // :45
+                const float j0 = (fractf(bn_r + kGoldenRatio * (float)(128 * 0 + frame_mod)) * 2.0f - 1.0f) * 0.003f;
+                float su = pu + j0, sv = pv + j0; // :46
+                for (int i = 0; i < samples; i++) {
+                    const float ji = (fractf(bn_r + kGoldenRatio * (float)(128 * (i + 1) + frame_mod)) * 2.0f - 1.0f) * 0.003f;
+                    su -= du + ji; // :48
+                    sv -= dv + ji;
+                    const bool inside = su >= 0.0f && su <= 1.0f && sv >= 0.0f && sv <= 1.0f;
+                    if (!inside) continue;
+                    const float sd = bilinear1(depth, W, H, su, sv);
+                    if (sd != 1.0f) continue; // :50
+                    V3 sr = v3(light.color[0], light.color[1], light.color[2]) * light.intensity * absorption;
+                    if (light.type == 0) { // LUZ_LIGHT_TYPE_POINT, :52-55
+                        const V3 wp = depth_to_world(scene, su, sv, sd);
+                        sr = sr * (5.0f / length(wp - lpos));
+                    }
+                    radiance = radiance + sr;
+                }
+            }
+            float* px = light_inout + 4 * ((size_t)y * W + x); // :59-61
+            px[0] += radiance.x;
+            px[1] += radiance.y;
+            px[2] += radiance.z;
+            px[3] += 0.0f;
+        }
+    }
+    return 0;
+}
+
+
 // present.frag:27-35, :85-95 (imageType 0, debug overlay alpha 0), BGRA8_unorm target
 int orc_compose_pass(uint32_t width, uint32_t height, const float* light_in, uint8_t* out_bgra8) {
     const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;

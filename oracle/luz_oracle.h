@@ -86,6 +86,12 @@ int orc_taa_pass(const luzw_scene_block* scene, uint32_t width, uint32_t height,
                  const float* history, const float* depth, int reconstruct, uint32_t y0, uint32_t y1,
                  float* out_rgba32f);
 
+/* screenSpaceVolumetricLight.comp main() over rows [y0, y1): adds into light_inout (full frame RGBA32F). */
+int orc_volumetric_screen_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                               uint32_t width, uint32_t height, const float* depth, const uint8_t* blue_noise_rgba8,
+                               uint32_t bn_w, uint32_t bn_h, uint32_t frame, uint32_t y0, uint32_t y1,
+                               float* light_inout);
+
 /* present.frag imageType 0 -> BGRA8. */
 int orc_compose_pass(uint32_t width, uint32_t height, const float* light_in, uint8_t* out_bgra8);
 

@@ -56,6 +56,8 @@ def lib():
                                      vp, u32, vp]
         L.orc_taa_pass.restype = i32
         L.orc_taa_pass.argtypes = [vp, u32, u32, vp, vp, vp, i32, u32, u32, vp]
+        L.orc_volumetric_screen_pass.restype = i32
+        L.orc_volumetric_screen_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, u32, u32, u32, u32, vp]
         L.orc_compose_pass.restype = i32
         L.orc_compose_pass.argtypes = [u32, u32, vp, vp]
         L.orc_gbuffer_pass.restype = i32
@@ -187,6 +189,20 @@ def taa_pass(scene, light_in, history, depth, reconstruct=True, rows=None):
     depth = np.ascontiguousarray(depth, np.float32)
     rc = lib().orc_taa_pass(_p(scene), w, h, _p(light_in), _p(history), _p(depth), 1 if reconstruct else 0, y0, y1,
                             _p(out))
+    assert rc == 0
+    return out
+
+
+def volumetric_screen_pass(scene, light, depth, blue_noise, frame, extra_lights=None, rows=None):
+    """screenSpaceVolumetricLight.comp over rows: returns a copy of `light` with the shafts added."""
+    h, w = depth.shape
+    y0, y1 = rows if rows else (0, h)
+    out = np.array(light, np.float32, copy=True, order="C")
+    depth = np.ascontiguousarray(depth, np.float32)
+    bn = np.ascontiguousarray(blue_noise, np.uint8)
+    n_extra = len(extra_lights) if extra_lights is not None else 0
+    rc = lib().orc_volumetric_screen_pass(_p(scene), _p(extra_lights) if n_extra else None, n_extra, w, h, _p(depth),
+                                          _p(bn), bn.shape[1], bn.shape[0], frame, y0, y1, _p(out))
     assert rc == 0
     return out
 

@@ -232,3 +232,115 @@ def test_taa_first_frame_identity_and_wrap():
     pad = np.pad(img, ((1, 1), (1, 1), (0, 0)), mode="wrap")
     stack = np.stack([pad[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)])
     assert (out <= stack.max(0) + 1e-5).all() and (out >= stack.min(0) - 1e-5).all()
+
+
+def _numpy_volumetric_pixel(sb, depth, bn, x, y, frame):
+    """screenSpaceVolumetricLight.comp:22-62 for one pixel, written independently in numpy float32 scalars."""
+    f = np.float32
+    h, w = depth.shape
+    GOLDEN = f(2.118033988749895)
+    vp = np.array(list(sb.view_proj), np.float32).reshape(4, 4)  # [col][row]
+    ip = np.array(list(sb.inverse_proj), np.float32).reshape(4, 4)
+    iv = np.array(list(sb.inverse_view), np.float32).reshape(4, 4)
+
+    def mat_vec(m, v):
+        return [f(f(f(m[0][r] * v[0]) + f(m[1][r] * v[1])) + f(m[2][r] * v[2])) + f(m[3][r] * v[3]) for r in range(4)]
+
+    def tap(u, v):
+        xx, yy = f(f(u * f(w)) - f(0.5)), f(f(v * f(h)) - f(0.5))
+        x0, y0 = int(np.floor(xx)), int(np.floor(yy))
+        fx, fy = f(xx - f(x0)), f(yy - f(y0))
+        t = lambda i, j: depth[j % h, i % w]
+        top = f(t(x0, y0) + f(fx * f(t(x0 + 1, y0) - t(x0, y0))))
+        bot = f(t(x0, y0 + 1) + f(fx * f(t(x0 + 1, y0 + 1) - t(x0, y0 + 1))))
+        return f(top + f(fy * f(bot - top)))
+
+    def noise(i):
+        v = f(f(bn[y % bn.shape[0], x % bn.shape[1], 0]) / f(255.0)) + f(GOLDEN * f(128 * i + frame % 128))
+        v = f(v)
+        return f(f(f(f(v - np.floor(v)) * f(2.0)) - f(1.0)) * f(0.003))
+
+    pu, pv = f(f(x) / f(w)), f(f(y) / f(h))
+    rad = [f(0), f(0), f(0)]
+    for li in range(sb.num_lights):
+        L = sb.lights[li]
+        if L.volumetric_type != 1:
+            continue
+        lp = mat_vec(vp, [f(L.position[0]), f(L.position[1]), f(L.position[2]), f(1)])
+        if L.type == 2:
+            lp = mat_vec(vp, [f(-f(L.direction[k]) * f(10000.0)) for k in range(3)] + [f(1)])
+        lu, lv = f(f(f(lp[0] / lp[3]) * f(0.5)) + f(0.5)), f(f(f(lp[1] / lp[3]) * f(0.5)) + f(0.5))
+        n = L.volumetric_samples
+        absorption = f(f(L.volumetric_absorption) / f(1000.0))
+        inv_n = f(f(1.0) / f(n))
+        du, dv = f(f(pu - lu) * inv_n), f(f(pv - lv) * inv_n)
+        su, sv = f(pu + noise(0)), f(pv + noise(0))
+        for i in range(n):
+            j = noise(i + 1)
+            su, sv = f(su - f(du + j)), f(sv - f(dv + j))
+            if not (0.0 <= su <= 1.0 and 0.0 <= sv <= 1.0):
+                continue
+            sd = tap(su, sv)
+            if sd != f(1.0):
+                continue
+            sr = [f(f(f(L.color[k]) * f(L.intensity)) * absorption) for k in range(3)]
+            if L.type == 0:
+                view = mat_vec(ip, [f(f(su * f(2)) - f(1)), f(f(sv * f(2)) - f(1)), sd, f(1)])
+                view = [f(c / view[3]) for c in view]
+                wp = mat_vec(iv, view)
+                d = [f(wp[k] - f(L.position[k])) for k in range(3)]
+                dist = f(np.sqrt(f(f(f(d[0] * d[0]) + f(d[1] * d[1])) + f(d[2] * d[2]))))
+                k5 = f(f(5.0) / dist)
+                sr = [f(c * k5) for c in sr]
+            rad = [f(rad[k] + sr[k]) for k in range(3)]
+    return rad
+
+
+def test_volumetric_screen_pass_known_answers():
+    """screenSpaceVolumetricLight.comp:22-62: closed-form counts on constant depth, plus an independent numpy
+    float32 evaluation of single pixels of a real scene's depth buffer (bit-exact)."""
+    w, h = 64, 48
+    bn = S.blue_noise()
+    sb = wire.SceneBlock()
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    for name in ("view_proj", "inverse_proj", "inverse_view"):
+        S.set_mat(getattr(sb, name), ident)
+    sb.num_lights = 2
+    spot, off = sb.lights[0], sb.lights[1]
+    for k in range(3):
+        spot.color[k], off.color[k] = (1.0, 0.5, 0.25)[k], 1.0
+        spot.position[k] = 0.0  # view_proj = I: lightUV = (0.5, 0.5)
+    spot.intensity, spot.type, spot.volumetric_type = 4.0, wire.LIGHT_SPOT, 1
+    spot.volumetric_samples, spot.volumetric_absorption = 8, 0.5
+    off.intensity, off.type, off.volumetric_type, off.volumetric_samples = 9.0, wire.LIGHT_POINT, 0, 128  # Disabled: skipped (:32)
+    light = np.full((h, w, 4), 0.25, np.float32)
+    # all background: every one of the 8 steps between an interior pixel and the screen centre counts (:48-57)
+    out = O.volumetric_screen_pass(sb, light, np.ones((h, w), np.float32), bn, 5)
+    c = np.float32(np.float32(4.0) * np.float32(np.float32(0.5) / np.float32(1000.0)))
+    rad = np.float32(0.0)
+    for _ in range(8):
+        rad = np.float32(rad + c)  # radiance is summed from zero, then added to the pixel (:29, :59-61)
+    assert out[20, 40, 0] == np.float32(np.float32(0.25) + rad) and out[20, 40, 3] == 0.25
+    assert abs(float(out[20, 40, 1]) - (0.25 + 8 * 2.0 * 0.0005)) < 1e-6
+    assert abs(float(out[20, 40, 0]) - (0.25 + 8 * 4.0 * 0.0005)) < 1e-6
+    # no background anywhere: nothing is added (:50)
+    out = O.volumetric_screen_pass(sb, light, np.full((h, w), 0.5, np.float32), bn, 5)
+    assert np.array_equal(out, light)
+    # rows outside [y0, y1) are untouched
+    out = O.volumetric_screen_pass(sb, light, np.ones((h, w), np.float32), bn, 5, rows=(10, 12))
+    assert np.array_equal(out[:10], light[:10]) and np.array_equal(out[12:], light[12:]) and (out[10:12, :, 0] > 0.25).all()
+    # a real depth buffer, all three light types, against the independent numpy evaluation
+    sc = S.synthetic_scene(w, h, grid=3, n_lights=3, light_samples=0, ao_samples=0, eye=(9, 2.5, 11))
+    world = O.World(sc["meshes"], sc["instances"])
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h)
+    assert 0.1 < float((gb.depth == 1.0).mean()) < 0.9
+    for i in range(3):
+        sc["scene"].lights[i].volumetric_type = 1
+        sc["scene"].lights[i].volumetric_samples = (24, 16, 12)[i]
+        sc["scene"].lights[i].volumetric_absorption = 0.5
+    zero = np.zeros((h, w, 4), np.float32)
+    out = O.volumetric_screen_pass(sc["scene"], zero, gb.depth, bn, 77)
+    assert float(out[..., :3].max()) > 0.0 and np.all(out[..., 3] == 0.0)
+    for (x, y) in [(0, 0), (63, 47), (31, 5), (10, 30), (50, 20), (5, 44)]:
+        exp = _numpy_volumetric_pixel(sc["scene"], gb.depth, bn, x, y, 77)
+        assert [float(v) for v in out[y, x, :3]] == [float(v) for v in exp], (x, y)
