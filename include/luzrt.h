@@ -103,6 +103,7 @@ typedef struct luzrt_timings {
     float gather_ms;  /* last luzrt_gather                                                    */
     float compose_ms; /* last luzrt_compose_pass   ("ComposePass", main.cpp:293)             */
     float volumetric_ms; /* last luzrt_volumetric_pass ("VolumetricLightPass", main.cpp:274)    */
+    float shadow_map_ms; /* last luzrt_shadow_map_pass ("ShadowMaps", main.cpp:260)              */
 } luzrt_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
@@ -194,15 +195,31 @@ LUZRT_API int luzrt_set_debug(luzrt_ctx* ctx, uint32_t flags);
  * (plus the rows TAA's 3x3 taps need). */
 LUZRT_API int luzrt_light_pass(luzrt_ctx* ctx, uint32_t frame);
 
+/* == the loop over DeferredRenderer::ShadowMapPass(light, scene, gpuScene)
+ * of RenderFrame (main.cpp:260-264, DeferredRenderer.cpp:268-291; shadowMap.vert/.geom/.frag): renders
+ * the D32F shadow map of every light of the current scene block that is sampled on this path -- lights
+ * with shadowMap != -1 when scene.shadowType == 2, and lights with volumetricType == 2 -- at
+ * resolution^2 texels (scene->shadowResolution, default 1024, AssetManager.hpp:287): six cube-face
+ * layers of |light.position - fragPos| / zFar for point lights, one layer of gl_FragCoord.z under the
+ * orthographic light.viewProj[0] for spot / directional lights.  There is no rasteriser here: one
+ * closest-hit ray per texel centre through the TLAS, keeping only the triangles the pipeline's
+ * front-face culling keeps (see csrc/shadow_map.cu).  Call after luzrt_set_scene + luzrt_tlas_build
+ * and before luzrt_light_pass / luzrt_volumetric_pass of the frame; both fail with LUZRT_E_STATE if
+ * the maps are older than the scene block or the TLAS.  In light.shadowMap only "-1 / not -1" matters
+ * (the reference stores a bindless texture index there, GPUScene.cpp:329). */
+LUZRT_API int luzrt_shadow_map_pass(luzrt_ctx* ctx, uint32_t resolution);
+/* Blocking read-back of light `light_index`'s map: layers * resolution^2 floats, layer-major, row 0 = top. */
+LUZRT_API int luzrt_read_shadow_map(luzrt_ctx* ctx, uint32_t light_index, void* dst, size_t bytes);
+
 /* == the block `if (gpuScene.AnyVolumetricLight())` of RenderFrame
- * (main.cpp:274-279), i.e. DeferredRenderer::ScreenSpaceVolumetricLightPass(gpuScene, frame)
- * (DeferredRenderer.cpp:294-307, screenSpaceVolumetricLight.comp:22-62): adds the screen-space
- * light shafts of every light with volumetricType == 1 into lightA, after luzrt_light_pass and
- * before luzrt_taa_pass.  A no-op when the scene block has no such light (== AnyVolumetricLight()
- * false).  The march reads depth anywhere in the frame: with world > 1, luzrt_set_gbuffer /
- * luzrt_prefetch_gbuffer / luzrt_gbuffer_pass fill the whole depth plane on every rank while the
- * scene block set by luzrt_set_scene has such a light.  Lights with volumetricType == 2
- * (shadow-map volumetrics, shadowMapVolumetricLight.comp) are rejected with LUZRT_E_INVALID. */
+ * (main.cpp:274-279): DeferredRenderer::ScreenSpaceVolumetricLightPass(gpuScene, frame)
+ * (DeferredRenderer.cpp:294-307, screenSpaceVolumetricLight.comp:22-62) for the lights with
+ * volumetricType == 1, then DeferredRenderer::ShadowMapVolumetricLightPass (DeferredRenderer.cpp:309-322,
+ * shadowMapVolumetricLight.comp:42-74) for the lights with volumetricType == 2; both add into lightA,
+ * after luzrt_light_pass and before luzrt_taa_pass.  A no-op when the scene block has no such light
+ * (== AnyVolumetricLight() false).  Both passes read depth outside the rows a rank shades: with
+ * world > 1, luzrt_set_gbuffer / luzrt_prefetch_gbuffer / luzrt_gbuffer_pass fill the whole depth
+ * plane on every rank while the scene block set by luzrt_set_scene has such a light. */
 LUZRT_API int luzrt_volumetric_pass(luzrt_ctx* ctx, uint32_t frame);
 
 /* == DeferredRenderer::TAAPass with scene->taaEnabled (DeferredRenderer.cpp:425-445,

@@ -59,7 +59,7 @@ struct Texture {
     uint2 size{0, 0};
 };
 
-enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_VOLUMETRIC, EV_COUNT };
+enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_VOLUMETRIC, EV_SHADOWMAP, EV_COUNT };
 
 } // namespace
 
@@ -99,6 +99,14 @@ struct luzrt_ctx {
     int n_vol_lights = 0;
     bool need_full_depth = false; // screen-space volumetrics read depth anywhere in the frame
     bool has_shadow_map_volumetric = false;
+    // shadow maps: one per light that needs it, re-rendered by luzrt_shadow_map_pass
+    std::vector<luzw_light_block> host_lights; // the lights of the current scene block
+    std::vector<float*> shadow_data;           // per light (grow-only device buffers)
+    std::vector<size_t> shadow_cap;            // floats
+    std::vector<ShadowMapRec> host_shadow_recs;
+    ShadowMapRec* d_shadow_recs = nullptr;
+    size_t shadow_recs_cap = 0;
+    bool shadow_maps_current = false; // rendered for the current scene block and TLAS
 
     std::vector<Blas> blas;
     BuildScratch scratch;
@@ -339,7 +347,9 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs};
+    for (float* p : c->shadow_data)
+        if (p) cudaFree(p);
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < EV_COUNT; i++)
@@ -638,6 +648,7 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     ev_end(c, EV_TLAS);
     c->n_inst = count;
     c->have_tlas = true;
+    c->shadow_maps_current = false; // the maps were rendered from the previous TLAS
     c->last_blas.resize(count);
     for (uint32_t i = 0; i < count; i++) c->last_blas[i] = instances[i].blas;
     if (c->tlas.levels.size() + max_blas_levels + 3 > LUZ_STACK_SIZE)
@@ -657,11 +668,12 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
     const int n = s->num_lights + (int)n_extra;
     std::vector<LightRec> recs((size_t)std::max(n, 1));
     std::vector<VolLight> vols;
+    c->host_lights.resize((size_t)n);
+    c->shadow_maps_current = false; // the reference re-renders every map every frame (main.cpp:260-264)
     uint32_t shadow_bits = 0;
     for (int i = 0; i < n; i++) {
         const luzw_light_block& l = i < LUZW_MAX_LIGHTS ? s->lights[i] : extra[i - LUZW_MAX_LIGHTS];
-        if (s->shadow_type == LUZW_SHADOW_MAP && l.shadow_map != -1)
-            return fail(c, LUZRT_E_INVALID, "shadow-map shadows (shadowType 2) are outside this path");
+        c->host_lights[i] = l;
         LightRec& r = recs[i];
         r.color_intensity = make_float4(l.color[0], l.color[1], l.color[2], l.intensity);
         r.position_inner = make_float4(l.position[0], l.position[1], l.position[2], l.inner_angle);
@@ -688,7 +700,7 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
     c->need_full_depth = false;
     c->has_shadow_map_volumetric = false;
     for (const VolLight& v : vols) {
-        if (v.volumetric_type == LUZW_VOLUMETRIC_SCREEN_SPACE) c->need_full_depth = true;
+        c->need_full_depth = true; // both passes tap depth outside the rows a rank shades
         if (v.volumetric_type == LUZW_VOLUMETRIC_SHADOW_MAP) c->has_shadow_map_volumetric = true;
     }
     if (!vols.empty()) {
@@ -937,7 +949,11 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     if (!c->have_tlas) return fail(c, LUZRT_E_STATE, "luzrt_tlas_build has not been called");
     if (!c->blue_noise) return fail(c, LUZRT_E_STATE, "luzrt_set_blue_noise has not been called");
     DeviceGuard g(c->device);
-    const bool masks = (c->debug & LUZRT_DEBUG_MASKS) != 0, stats = (c->debug & LUZRT_DEBUG_STATS) != 0;
+    const bool stats = (c->debug & LUZRT_DEBUG_STATS) != 0;
+    // the shadow-map variant of the kernel is compiled with and without (masks + stats) only
+    const bool masks = (c->debug & LUZRT_DEBUG_MASKS) != 0 || (stats && c->fc.shadow_type == LUZW_SHADOW_MAP);
+    if (c->fc.shadow_type == LUZW_SHADOW_MAP && !c->shadow_maps_current)
+        return fail(c, LUZRT_E_STATE, "shadowType 2: luzrt_shadow_map_pass has not been called for this scene block");
     const size_t px = (size_t)c->w * c->h;
     if (masks) {
         const size_t sw = std::max<size_t>((c->shadow_bits + 31) / 32, 1);
@@ -969,6 +985,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.ao_words = (uint32_t)c->ao_mask_words;
     a.stats = c->d_stats;
     a.lit_counters = c->d_lit;
+    a.shadow_maps = c->d_shadow_recs;
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
     CU(c, wait_gather(c, a.out));
@@ -982,13 +999,128 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     return LUZRT_OK;
 }
 
+namespace {
+// 4x4 inverse (column-major) in double by Gauss-Jordan with partial pivoting; false if singular
+bool invert4(const float* m, float* out) {
+    double a[4][8];
+    for (int r = 0; r < 4; r++)
+        for (int col = 0; col < 4; col++) {
+            a[r][col] = m[col * 4 + r];
+            a[r][4 + col] = r == col ? 1.0 : 0.0;
+        }
+    for (int i = 0; i < 4; i++) {
+        int piv = i;
+        for (int r = i + 1; r < 4; r++)
+            if (fabs(a[r][i]) > fabs(a[piv][i])) piv = r;
+        if (a[piv][i] == 0.0 || a[piv][i] != a[piv][i]) return false;
+        if (piv != i)
+            for (int k = 0; k < 8; k++) std::swap(a[i][k], a[piv][k]);
+        const double d = a[i][i];
+        for (int k = 0; k < 8; k++) a[i][k] /= d;
+        for (int r = 0; r < 4; r++)
+            if (r != i) {
+                const double f = a[r][i];
+                for (int k = 0; k < 8; k++) a[r][k] -= f * a[i][k];
+            }
+    }
+    for (int r = 0; r < 4; r++)
+        for (int col = 0; col < 4; col++) out[col * 4 + r] = (float)a[r][4 + col];
+    return true;
+}
+// determinant of rows (r0, r1, r2) x columns 0..2 of a column-major mat4
+double det3_rows(const float* m, int r0, int r1, int r2) {
+    const int rows[3] = {r0, r1, r2};
+    double a[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int col = 0; col < 3; col++) a[i][col] = m[col * 4 + rows[i]];
+    return a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+           a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+}
+} // namespace
+
+int luzrt_shadow_map_pass(luzrt_ctx* c, uint32_t resolution) {
+    if (!c) return LUZRT_E_INVALID;
+    if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
+    if (!c->have_tlas) return fail(c, LUZRT_E_STATE, "luzrt_tlas_build has not been called");
+    REQUIRE(c, resolution >= 1 && resolution <= 16384, "shadow map resolution must be in [1, 16384]");
+    DeviceGuard g(c->device);
+    const size_t n = c->host_lights.size();
+    c->shadow_data.resize(std::max(c->shadow_data.size(), n), nullptr);
+    c->shadow_cap.resize(std::max(c->shadow_cap.size(), n), 0);
+    c->host_shadow_recs.assign(std::max<size_t>(n, 1), ShadowMapRec{});
+    ev_begin(c, EV_SHADOWMAP);
+    for (size_t i = 0; i < n; i++) {
+        const luzw_light_block& l = c->host_lights[i];
+        // the reference renders a map for every light every frame (main.cpp:260-264); only these are ever sampled
+        const bool needed = (c->fc.shadow_type == LUZW_SHADOW_MAP && l.shadow_map != -1) ||
+                            l.volumetric_type == LUZW_VOLUMETRIC_SHADOW_MAP;
+        if (!needed) continue;
+        ShadowMapArgs a{};
+        a.scene = TraceScene{c->tlas.nodes, c->d_recs, c->d_inst_boxes, c->min_node_lanes};
+        a.res = resolution;
+        a.is_cube = l.type == LUZW_LIGHT_POINT ? 1 : 0;
+        a.layers = a.is_cube ? 6u : 1u;
+        a.z_far = l.z_far;
+        memcpy(a.eye, l.position, 12);
+        if (a.is_cube) {
+            for (int f = 0; f < 6; f++) {
+                const double d = det3_rows(l.view_proj[f], 0, 1, 3);
+                if (d == 0.0 || d != d) return fail(c, LUZRT_E_INVALID, "light %zu: viewProj[%d] is singular", i, f);
+                a.cull_sign[f] = d < 0.0 ? -1.0f : 1.0f;
+            }
+        } else {
+            const float* m = l.view_proj[0];
+            if (m[3] != 0.0f || m[7] != 0.0f || m[11] != 0.0f || m[15] != 1.0f)
+                return fail(c, LUZRT_E_INVALID, "light %zu: viewProj[0] of a spot/directional light must be orthographic "
+                                                "(GPUScene.cpp:278-310)", i);
+            const double d = det3_rows(m, 0, 1, 2);
+            if (d == 0.0 || d != d || !invert4(m, a.inv_view_proj))
+                return fail(c, LUZRT_E_INVALID, "light %zu: viewProj[0] is singular", i);
+            a.cull_sign[0] = d < 0.0 ? -1.0f : 1.0f;
+        }
+        const size_t need = (size_t)a.layers * resolution * resolution;
+        int rc;
+        if ((rc = grow(c, c->shadow_data[i], c->shadow_cap[i], need)) != LUZRT_OK) return rc;
+        a.out = c->shadow_data[i];
+        CU(c, launch_shadow_map(c->stream, a));
+        c->launches++;
+        ShadowMapRec& r = c->host_shadow_recs[i];
+        memcpy(r.view_proj, l.view_proj[0], 64);
+        r.data = c->shadow_data[i];
+        r.res = resolution;
+        r.layers = a.layers;
+        r.z_far = l.z_far;
+    }
+    int rc;
+    if ((rc = grow(c, c->d_shadow_recs, c->shadow_recs_cap, c->host_shadow_recs.size())) != LUZRT_OK) return rc;
+    CU(c, cudaMemcpyAsync(c->d_shadow_recs, c->host_shadow_recs.data(), c->host_shadow_recs.size() * sizeof(ShadowMapRec),
+                          cudaMemcpyHostToDevice, c->stream));
+    ev_end(c, EV_SHADOWMAP);
+    c->shadow_maps_current = true;
+    return LUZRT_OK;
+}
+
+int luzrt_read_shadow_map(luzrt_ctx* c, uint32_t light, void* dst, size_t bytes) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, dst, "dst is null");
+    if (!c->shadow_maps_current) return fail(c, LUZRT_E_STATE, "luzrt_shadow_map_pass has not been called for this scene block");
+    REQUIRE(c, light < c->host_shadow_recs.size() && c->host_shadow_recs[light].data, "this light has no shadow map");
+    const ShadowMapRec& r = c->host_shadow_recs[light];
+    const size_t need = (size_t)r.layers * r.res * r.res * sizeof(float);
+    REQUIRE(c, bytes >= need, "buffer too small for the shadow map");
+    DeviceGuard g(c->device);
+    CU(c, cudaMemcpyAsync(dst, r.data, need, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return LUZRT_OK;
+}
+
 int luzrt_volumetric_pass(luzrt_ctx* c, uint32_t frame) {
     if (!c) return LUZRT_E_INVALID;
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
     if (!c->have_scene) return fail(c, LUZRT_E_STATE, "luzrt_set_scene has not been called");
     if (c->n_vol_lights == 0) return LUZRT_OK; // AnyVolumetricLight() == false (main.cpp:275)
-    if (c->has_shadow_map_volumetric)
-        return fail(c, LUZRT_E_INVALID, "shadow-map volumetrics (volumetricType 2) are outside this path");
+    if (c->has_shadow_map_volumetric && !c->shadow_maps_current)
+        return fail(c, LUZRT_E_STATE, "volumetricType 2: luzrt_shadow_map_pass has not been called for this scene block");
     if (!c->blue_noise) return fail(c, LUZRT_E_STATE, "luzrt_set_blue_noise has not been called");
     DeviceGuard g(c->device);
     VolumetricArgs a{};
@@ -1004,8 +1136,17 @@ int luzrt_volumetric_pass(luzrt_ctx* c, uint32_t frame) {
     a.rows = shade_bands(c);
     CU(c, wait_gather(c, a.light));
     ev_begin(c, EV_VOLUMETRIC);
-    CU(c, launch_volumetric_screen(c->stream, a));
-    c->launches++;
+    a.shadow_maps = c->d_shadow_recs;
+    bool any_screen = false;
+    for (const luzw_light_block& l : c->host_lights) any_screen |= l.volumetric_type == LUZW_VOLUMETRIC_SCREEN_SPACE;
+    if (any_screen) { // DeferredRenderer::ScreenSpaceVolumetricLightPass
+        CU(c, launch_volumetric_screen(c->stream, a));
+        c->launches++;
+    }
+    if (c->has_shadow_map_volumetric) { // DeferredRenderer::ShadowMapVolumetricLightPass
+        CU(c, launch_volumetric_shadow_map(c->stream, a));
+        c->launches++;
+    }
     ev_end(c, EV_VOLUMETRIC);
     return LUZRT_OK;
 }
@@ -1107,7 +1248,7 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
         float ms[EV_COUNT] = {0};
         for (int i = 0; i < EV_COUNT; i++)
             if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], c->ev[i][0], c->ev[i][1]);
-        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC]};
+        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC], ms[EV_SHADOWMAP]};
         memcpy(dst, &t, sizeof(t));
         return LUZRT_OK;
     }

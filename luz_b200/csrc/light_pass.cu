@@ -48,7 +48,9 @@ __device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughne
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
-template <bool MASKS, bool STATS, int MIN_BLOCKS>
+// SMAP: the variant launched when scene.shadowType == SHADOW_TYPE_MAP (light.frag:147-165); kept out of the
+// ray-traced variants so that their register allocation is untouched.
+template <bool MASKS, bool STATS, int MIN_BLOCKS, bool SMAP = false>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
             int n_samples;
             int n_cand = -1; // < 0: rays descend from the TLAS root
             bool directional_or_shadowless = false;
+            float3 lposv = f3(0.0f, 0.0f, 0.0f);
+            int ltype = 0, lsmap = -1;
             if (is_ao) { // TraceAORays (light.frag:111-135)
                 O = fragPos + N * (camDist * 0.01f);
                 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
@@ -180,6 +184,11 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                 tMaxRay = length3(C);
                 n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
                 directional_or_shadowless = fc.shadow_type != LUZW_SHADOW_RAYTRACING;
+                if (SMAP) {
+                    lposv = lpos;
+                    ltype = L4.type;
+                    lsmap = L4.shadow_map;
+                }
             }
             // ---- the rays of this source ----
             float hits = 0.0f;
@@ -223,6 +232,8 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
             // shadow factor: RT with samples -> occluded fraction; RT with 0 samples -> 0; otherwise 1 (:166-168)
             float shadowFactor = directional_or_shadowless ? 1.0f : 0.0f;
             if (n_samples > 0) shadowFactor = hits / (float)n_samples;
+            if (SMAP && fc.shadow_type == LUZW_SHADOW_MAP && lsmap != -1) // light.frag:147-165
+                shadowFactor = shadow_map_factor(a.shadow_maps[base + li], ltype, lposv, fragPos, O);
             const float3 lcol = f3(lcolor.x, lcolor.y, lcolor.z);
             const float3 radiance = lcol * lcolor.w * attenuation * (1.0f - shadowFactor);
 
@@ -287,7 +298,12 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool m
         const char* e = getenv("LUZRT_LIGHT_MINB");
         return e ? atoi(e) : 6;
     }();
-    if (masks && stats)
+    if (args.fc.shadow_type == LUZW_SHADOW_MAP) {
+        if (masks || stats)
+            k_light_pass<true, true, 4, true><<<grid, 128, smem, stream>>>(a2);
+        else
+            k_light_pass<false, false, 4, true><<<grid, 128, smem, stream>>>(a2);
+    } else if (masks && stats)
         k_light_pass<true, true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (masks)
         k_light_pass<true, false, 4><<<grid, 128, smem, stream>>>(a2);

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include "common.cuh"
+#include "shadow_map.cuh"
 
 namespace luz {
 
@@ -27,6 +28,7 @@ struct LightArgs {
     unsigned long long* lit_counters; // 64 counters, 128 B apart
     uint32_t count_row_begin, count_row_end; // rows (relative to a band's first row) whose lit pixels are counted
     uint32_t cand_offset;                    // byte offset of the AO candidate lists in dynamic shared memory
+    const ShadowMapRec* shadow_maps;         // per light, scene order (read only when fc.shadow_type == LUZW_SHADOW_MAP)
 };
 
 struct TaaArgs {
@@ -77,9 +79,24 @@ struct VolumetricArgs {
     int n_lights;
     float4* light; // lightA, read-modify-write
     BandSet rows;  // the rows the light pass shaded (own bands + halo rows)
+    const ShadowMapRec* shadow_maps; // per light, scene order (shadow-map volumetrics)
+};
+
+// one shadow map (all its layers) of one light
+struct ShadowMapArgs {
+    TraceScene scene;
+    float* out; // layers * res * res
+    uint32_t res, layers;
+    int is_cube;
+    float eye[3]; // light.position (cube)
+    float z_far;
+    float inv_view_proj[16]; // inverse of light.viewProj[0], column-major (2-D)
+    float cull_sign[6];      // s_view per layer (shadow_map.cu)
 };
 
 cudaError_t launch_volumetric_screen(cudaStream_t stream, const VolumetricArgs& args);
+cudaError_t launch_volumetric_shadow_map(cudaStream_t stream, const VolumetricArgs& args);
+cudaError_t launch_shadow_map(cudaStream_t stream, const ShadowMapArgs& args);
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats);
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
 cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,

@@ -17,6 +17,9 @@ struct HitInfo {
     uint32_t inst; // index into the TLAS-ordered instance array
     uint32_t prim; // original triangle index inside the BLAS
     float bu, bv;  // barycentric weights of v0, v1
+    // input of trace_ray<.., FACE_CULL = true>: +1 / -1 = the sign s_view of the rasteriser view being emulated; a
+    // triangle is kept iff s_view * sign(det instance) * dot(d, (v1 - v0) x (v2 - v0)) > 0 (shadow_map.cu)
+    float cull_sign;
 };
 
 struct LocalStats {
@@ -254,7 +257,7 @@ __device__ __forceinline__ int collect_instances(const TraceScene& sc, const flo
 // (TLAS leaf order indices from collect_instances).  `stack` is LUZ_STACK_SIZE entries of caller storage.
 constexpr uint32_t kNoInstance = 0xFFFFFFFFu;
 
-template <bool CLOSEST, bool STATS>
+template <bool CLOSEST, bool STATS, bool FACE_CULL = false>
 __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo, const float3 wd, const float tmin,
                                           float tmax, HitInfo* hit, LocalStats* st, uint2* stack,
                                           const uint32_t* cand = nullptr, const int cand_stride = 0,
@@ -281,6 +284,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     uint2 tgroup = make_uint2(0u, 0u);
     uint32_t pending = kNoInstance; // instance to enter at the top of the loop
     int ci = 0;
+    float face_sign = 0.0f; // FACE_CULL: cull_sign * sign(det of the current instance's matrix)
     rs = make_ray_space(o, d);
     inv_dd = 0.0f; // only triangles need it, and they live in object space
     if (from_root) ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
@@ -298,6 +302,12 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             d = xform_dir(r0, r1, r2, wd);
             rs = make_ray_space(o, d);
             inv_dd = fast_rcp(dot3_fma(d, d));
+            if (FACE_CULL) {
+                // det of the world->object rows has the sign of det of the instance matrix
+                const float det = r0.x * (r1.y * r2.z - r1.z * r2.y) - r0.y * (r1.x * r2.z - r1.z * r2.x) +
+                                  r0.z * (r1.x * r2.y - r1.y * r2.x);
+                face_sign = det < 0.0f ? -hit->cull_sign : hit->cull_sign;
+            }
             nodes = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
             tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
             cur_inst = pending;
@@ -350,6 +360,11 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 if (STATS) st->tris++;
                 float t, bu, bv;
                 if (tri_test(p0, p1, p2, o, d, inv_dd, tmin, tmax, t, bu, bv)) {
+                    if (FACE_CULL) { // front faces (in the framebuffer of the emulated view) are not rasterised
+                        const float3 e1 = f3(p1.x - p0.x, p1.y - p0.y, p1.z - p0.z), e2 = f3(p2.x - p0.x, p2.y - p0.y, p2.z - p0.z);
+                        const float3 n = cross3(e1, e2);
+                        if (!(face_sign * dot3(d, n) > 0.0f)) continue;
+                    }
                     if (!CLOSEST) return true;
                     tmax = t;
                     found = true;

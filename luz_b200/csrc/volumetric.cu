@@ -98,7 +98,62 @@ __global__ void __launch_bounds__(128) k_volumetric_screen(const VolumetricArgs 
     *px = v;
 }
 
+// shadowMapVolumetricLight.comp:42-74, dispatched by DeferredRenderer::ShadowMapVolumetricLightPass
+// (DeferredRenderer.cpp:309-322) right after the screen-space pass: per pixel and per light with volumetricType ==
+// VOLUMETRIC_TYPE_SHADOW_MAP, 128 steps along the segment camera -> (1.094 x) the pixel's world position, each adding
+// (1 - shadow) * color * intensity * 0.000005, shadow from the light's shadow map.  weight / samples / density are
+// the shader's hard-coded locals (:57-60), not the LightBlock fields of the same names.
+__global__ void __launch_bounds__(128) k_volumetric_shadow_map(const VolumetricArgs a) {
+    const FrameConst& fc = a.fc;
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t r = blockIdx.y * 4 + (threadIdx.x >> 5);
+    if (x >= fc.width || r >= a.rows.rows) return;
+    const uint32_t y = band_row(fc, a.rows, blockIdx.z, r);
+    const int W = (int)fc.width, H = (int)fc.height;
+
+    const float pu = (float)x / (float)W, pv = (float)y / (float)H; // :48
+    const float pixelDepth = depth_bilinear(a.depth, W, H, pu, pv);  // texture() at a texel corner: a 2x2 average
+    const float3 worldPos = depth_to_world(fc, pu, pv, pixelDepth);
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const uchar4 bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+    const float bn_r = (float)bn8.x / 255.0f;
+    const float noise0 = fractf(bn_r + kGoldenRatio * (float)fc.frame_mod);
+    float3 radiance = f3(0.0f, 0.0f, 0.0f);
+
+    for (int li = 0; li < a.n_lights; li++) {
+        const VolLight L = a.lights[li];
+        if (L.volumetric_type != LUZW_VOLUMETRIC_SHADOW_MAP) continue;
+        const ShadowMapRec& m = a.shadow_maps[L.light_index];
+        const float3 lpos = f3(L.position_type.x, L.position_type.y, L.position_type.z);
+        const int type = __float_as_int(L.position_type.w);
+        const float3 lcol = f3(L.color_intensity.x, L.color_intensity.y, L.color_intensity.z);
+        const float weight = 0.000005f, decay = 1.0f, density = 1.094f;
+        const int samples = 128;
+        const float3 deltaPos = (camPos - worldPos) * density * (1.0f / (float)samples);
+        const float off = noise0 * length3(deltaPos);
+        float3 samplePos = f3(camPos.x + off, camPos.y + off, camPos.z + off);
+        for (int i = 0; i < samples; i++) {
+            samplePos = samplePos - deltaPos;
+            const float sh = shadow_map_factor(m, type, lpos, samplePos, samplePos);
+            radiance = radiance + (1.0f - sh) * lcol * L.color_intensity.w * weight * decay;
+        }
+    }
+    float4* px = a.light + (size_t)storage_row(fc, y) * fc.width + x;
+    float4 v = *px;
+    v.x += radiance.x;
+    v.y += radiance.y;
+    v.z += radiance.z;
+    *px = v;
+}
+
 } // namespace
+
+cudaError_t launch_volumetric_shadow_map(cudaStream_t stream, const VolumetricArgs& args) {
+    if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0 || args.n_lights == 0) return cudaSuccess;
+    const dim3 grid((args.fc.width + 31) / 32, (args.rows.rows + 3) / 4, args.rows.n_bands);
+    k_volumetric_shadow_map<<<grid, 128, 0, stream>>>(args);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_volumetric_screen(cudaStream_t stream, const VolumetricArgs& args) {
     if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0 || args.n_lights == 0) return cudaSuccess;

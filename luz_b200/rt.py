@@ -24,7 +24,8 @@ EXPORTS = [
     "luzrt_gather", "luzrt_compose_pass", "luzrt_swap_light_history", "luzrt_read", "luzrt_device_ptr",
     "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_bands", "luzrt_read_owned",
     "luzrt_prefetch_gbuffer", "luzrt_flip_gbuffer", "luzrt_read_owned_async", "luzrt_read_wait",
-    "luzrt_probe_read_bandwidth", "luzrt_volumetric_pass",
+    "luzrt_probe_read_bandwidth", "luzrt_volumetric_pass", "luzrt_shadow_map_pass",
+    "luzrt_read_shadow_map",
 ]
 
 
@@ -67,6 +68,8 @@ def load_library():
         "luzrt_light_pass": (i32, [vp, u32]),
         "luzrt_taa_pass": (i32, [vp, i32]),
         "luzrt_volumetric_pass": (i32, [vp, u32]),
+        "luzrt_shadow_map_pass": (i32, [vp, u32]),
+        "luzrt_read_shadow_map": (i32, [vp, u32, vp, C.c_size_t]),
         "luzrt_gather": (i32, [vp]),
         "luzrt_compose_pass": (i32, [vp, C.c_float]),
         "luzrt_swap_light_history": (i32, [vp]),
@@ -204,6 +207,14 @@ class LuzRT:
 
     def light_pass(self, frame):
         self._ck(self.lib.luzrt_light_pass(self.h, frame))
+
+    def shadow_map_pass(self, resolution=1024):
+        self._ck(self.lib.luzrt_shadow_map_pass(self.h, resolution))
+
+    def read_shadow_map(self, light, resolution, layers):
+        out = np.zeros((layers, resolution, resolution), np.float32)
+        self._ck(self.lib.luzrt_read_shadow_map(self.h, light, out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
 
     def volumetric_pass(self, frame):
         self._ck(self.lib.luzrt_volumetric_pass(self.h, frame))

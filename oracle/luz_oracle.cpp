@@ -425,6 +425,83 @@ inline bool occluded(const orc_world* w, V3 o, V3 d, float tmin, float tmax, boo
 }
 
 // ------------------------------------------------------------------------------------------
+// Shadow maps: the two texture() look-ups of light.frag:147-165 and
+// shadowMapVolumetricLight.comp:22-40.  D32F maps of res^2 texels: six cube-face layers
+// (+X -X +Y -Y +Z -Z) holding |light.position - fragPos| / zFar for point lights, one layer of
+// gl_FragCoord.z under the orthographic light.viewProj[0] otherwise; cleared to 1.0.  LINEAR /
+// REPEAT sampler (VulkanWrapper.cpp:2429-2461): bilinear taps as nested lerps a + w * (b - a);
+// the 2-D tap wraps; the cube tap picks the face by the Vulkan rules (major axis, z over y over
+// x on ties, sc / tc table) and clamps its 2x2 footprint to the face (no blending with the
+// adjacent face at cube edges: documented deviation).
+// ------------------------------------------------------------------------------------------
+const orc_shadow_map* g_shadow_maps = nullptr;
+uint32_t g_n_shadow_maps = 0;
+
+inline int wrap_mod(int i, int n) {
+    int r = i % n;
+    return r < 0 ? r + n : r;
+}
+inline float lerp1(float a, float b, float w) { return a + w * (b - a); }
+
+float shadow_tap_2d(const float* d, int res, float u, float v) {
+    const float x = u * (float)res - 0.5f, y = v * (float)res - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    if (std::isnan(fx0) || std::isnan(fy0)) return std::numeric_limits<float>::quiet_NaN();
+    const int ix = (int)fminf(fmaxf(fx0, -1.0e9f), 1.0e9f), iy = (int)fminf(fmaxf(fy0, -1.0e9f), 1.0e9f);
+    const int x0 = wrap_mod(ix, res), y0 = wrap_mod(iy, res), x1 = wrap_mod(ix + 1, res), y1 = wrap_mod(iy + 1, res);
+    const float top = lerp1(d[(size_t)y0 * res + x0], d[(size_t)y0 * res + x1], fx);
+    const float bot = lerp1(d[(size_t)y1 * res + x0], d[(size_t)y1 * res + x1], fx);
+    return lerp1(top, bot, fy);
+}
+
+float shadow_tap_cube(const float* d, int res, V3 r) {
+    const float ax = fabsf(r.x), ay = fabsf(r.y), az = fabsf(r.z);
+    int face;
+    float sc, tc, ma;
+    if (az >= ax && az >= ay) {
+        face = r.z < 0.0f ? 5 : 4;
+        sc = r.z < 0.0f ? -r.x : r.x;
+        tc = -r.y;
+        ma = az;
+    } else if (ay >= ax) {
+        face = r.y < 0.0f ? 3 : 2;
+        sc = r.x;
+        tc = r.y < 0.0f ? -r.z : r.z;
+        ma = ay;
+    } else {
+        face = r.x < 0.0f ? 1 : 0;
+        sc = r.x < 0.0f ? r.z : -r.z;
+        tc = -r.y;
+        ma = ax;
+    }
+    const float u = 0.5f * (sc / ma) + 0.5f, v = 0.5f * (tc / ma) + 0.5f;
+    const float x = u * (float)res - 0.5f, y = v * (float)res - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    if (std::isnan(fx0) || std::isnan(fy0)) return std::numeric_limits<float>::quiet_NaN();
+    auto cl = [&](float f) { return std::min(std::max((int)fminf(fmaxf(f, -1.0e9f), 1.0e9f), 0), res - 1); };
+    const int x0 = cl(fx0), y0 = cl(fy0), x1 = cl(fx0 + 1.0f), y1 = cl(fy0 + 1.0f);
+    const float* f = d + (size_t)face * res * res;
+    const float top = lerp1(f[(size_t)y0 * res + x0], f[(size_t)y0 * res + x1], fx);
+    const float bot = lerp1(f[(size_t)y1 * res + x0], f[(size_t)y1 * res + x1], fx);
+    return lerp1(top, bot, fy);
+}
+
+// the SHADOW_TYPE_MAP branch of EvaluateShadow (light.frag:147-165); 1 = in shadow
+float shadow_map_factor(const luzw_light_block& light, const orc_shadow_map& m, V3 fragPos, V3 shadowOrigin) {
+    const V3 lpos = v3(light.position[0], light.position[1], light.position[2]);
+    if (light.type == LUZW_LIGHT_POINT) {
+        const V3 lightToFrag = fragPos - lpos;
+        const float shadowDepth = shadow_tap_cube(m.data, (int)m.res, lightToFrag);
+        return (length(lightToFrag) - 0.05f >= shadowDepth * light.z_far) ? 1.0f : 0.0f;
+    }
+    const V4 fragInLight = mul(light.view_proj[0], V4{shadowOrigin.x, shadowOrigin.y, shadowOrigin.z, 1.0f});
+    const float shadowDepth = shadow_tap_2d(m.data, (int)m.res, fragInLight.x * 0.5f + 0.5f, fragInLight.y * 0.5f + 0.5f);
+    return (fragInLight.z >= shadowDepth) ? 1.0f : 0.0f;
+}
+
+// ------------------------------------------------------------------------------------------
 // light.frag
 // ------------------------------------------------------------------------------------------
 
@@ -672,9 +749,11 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
                    int exhaustive, uint32_t y0, uint32_t y1, float* out, uint32_t* shadow_mask,
                    uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words, orc_stats* stats) {
     const int numLights = scene->num_lights + (int)n_extra;
-    if (scene->shadow_type == LUZW_SHADOW_MAP) {
+    if (scene->shadow_type == LUZW_SHADOW_MAP) { // the maps come from orc_bind_shadow_maps
         for (int i = 0; i < numLights; i++)
-            if (light_at(scene, extra_lights, i).shadow_map != -1) return -1; // shadow maps: out of scope
+            if (light_at(scene, extra_lights, i).shadow_map != -1 &&
+                ((uint32_t)i >= g_n_shadow_maps || !g_shadow_maps[i].data))
+                return -1;
     }
     uint64_t tot_rays = 0, tot_occl = 0, tot_lit = 0;
     int frame_signed = (int)frame;
@@ -764,8 +843,10 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
                         shadowFactor = trace_shadow_ray(c, shadowOrigin, Lr, (float)light.num_shadow_samples,
                                                         light.radius, smask, shadow_bit);
                         shadow_bit += (uint32_t)(light.num_shadow_samples > 0 ? light.num_shadow_samples : 0);
+                    } else if (scene->shadow_type == LUZW_SHADOW_MAP && light.shadow_map != -1) {
+                        shadowFactor = shadow_map_factor(light, g_shadow_maps[i], fragPos, shadowOrigin); // :147-165
                     } else {
-                        shadowFactor = 1.0f; // :166-168 (shadow-map branch rejected above)
+                        shadowFactor = 1.0f; // :166-168
                     }
                 }
                 const V3 lcol = v3(light.color[0], light.color[1], light.color[2]);
@@ -1044,6 +1125,195 @@ int orc_volumetric_screen_pass(const luzw_scene_block* scene, const luzw_light_b
             px[1] += radiance.y;
             px[2] += radiance.z;
             px[3] += 0.0f;
+        }
+    }
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// DeferredRenderer::ShadowMapPass (DeferredRenderer.cpp:268-291) with shadowMap.vert:15-17,
+// shadowMap.geom:17-38, shadowMap.frag:12-18, restated per texel: every triangle goes through
+// the pipeline's own steps -- world position = modelMat * pos (vert), clip = light.viewProj[f] *
+// world (geom), FRONT-face culling with front = counter-clockwise in framebuffer space
+// (`.cullFront = true`, DeferredRenderer.cpp:100; VulkanWrapper.cpp:941-946): the framebuffer
+// area of the Vulkan spec has the sign of -det[c0; c1; c2] over (x, y, w), so a triangle is
+// front-facing, and dropped, iff that determinant is negative -- and the fragment of a texel is
+// found with a ray through the texel centre (exhaustive over all triangles), depth test LESS
+// against the clear value 1.0, no depth clamp.  Point lights: the texel-centre direction of layer
+// f is the Vulkan cube-face table inverted (light.viewProj[f] of GPUScene.cpp:268-276 maps to
+// exactly that table) and the value is |light.position - fragPos| / zFar; others: the ray runs
+// from NDC z = 0 to z = 1 of light.viewProj[0] and the value is its parameter (= gl_FragCoord.z).
+// ------------------------------------------------------------------------------------------
+namespace {
+bool invert4d(const float* m, double inv[16]) {
+    double a[4][8];
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+            a[r][c] = m[c * 4 + r];
+            a[r][4 + c] = r == c ? 1.0 : 0.0;
+        }
+    for (int i = 0; i < 4; i++) {
+        int piv = i;
+        for (int r = i + 1; r < 4; r++)
+            if (fabs(a[r][i]) > fabs(a[piv][i])) piv = r;
+        if (a[piv][i] == 0.0 || std::isnan(a[piv][i])) return false;
+        if (piv != i)
+            for (int k = 0; k < 8; k++) std::swap(a[i][k], a[piv][k]);
+        const double d = a[i][i];
+        for (int k = 0; k < 8; k++) a[i][k] /= d;
+        for (int r = 0; r < 4; r++)
+            if (r != i) {
+                const double f = a[r][i];
+                for (int k = 0; k < 8; k++) a[r][k] -= f * a[i][k];
+            }
+    }
+    for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) inv[c * 4 + r] = a[r][4 + c];
+    return true;
+}
+} // namespace
+
+int orc_shadow_map_pass(const luzw_light_block* light, const orc_world* world, uint32_t res, float* out) {
+    const bool cube = light->type == LUZW_LIGHT_POINT;
+    const int layers = cube ? 6 : 1;
+    double inv[16];
+    float invf[16];
+    if (!cube) {
+        if (!invert4d(light->view_proj[0], inv)) return -1;
+        for (int k = 0; k < 16; k++) invf[k] = (float)inv[k];
+    }
+    // world-space triangles once: modelMat * vec4(inPosition, 1) (shadowMap.vert:16)
+    struct WTri {
+        float p[3][3];
+    };
+    std::vector<WTri> tris;
+    for (const InstData& in : world->inst) {
+        const MeshData& md = world->meshes[in.mesh];
+        for (size_t t = 0; t + 2 < md.idx.size(); t += 3) {
+            WTri w;
+            for (int k = 0; k < 3; k++) {
+                const float* p = &md.pos[3 * (size_t)md.idx[t + k]];
+                const V4 wp = mul(in.m, V4{p[0], p[1], p[2], 1.0f});
+                w.p[k][0] = wp.x;
+                w.p[k][1] = wp.y;
+                w.p[k][2] = wp.z;
+            }
+            tris.push_back(w);
+        }
+    }
+    const V3 eye = v3(light->position[0], light->position[1], light->position[2]);
+    for (int layer = 0; layer < layers; layer++) {
+        const float* vp = light->view_proj[cube ? layer : 0];
+        // front-face culling per triangle, from its clip coordinates (shadowMap.geom:25, :33)
+        std::vector<const WTri*> kept;
+        for (const WTri& w : tris) {
+            double c[3][3];
+            for (int k = 0; k < 3; k++) {
+                const V4 cp = mul(vp, V4{w.p[k][0], w.p[k][1], w.p[k][2], 1.0f});
+                c[k][0] = cp.x;
+                c[k][1] = cp.y;
+                c[k][2] = cp.w;
+            }
+            const double D = c[0][0] * (c[1][1] * c[2][2] - c[1][2] * c[2][1]) -
+                             c[0][1] * (c[1][0] * c[2][2] - c[1][2] * c[2][0]) +
+                             c[0][2] * (c[1][0] * c[2][1] - c[1][1] * c[2][0]);
+            if (D > 0.0) kept.push_back(&w); // D < 0: front-facing, culled; D == 0: no area
+        }
+#pragma omp parallel for schedule(dynamic, 4) num_threads(orc_get_threads())
+        for (int y = 0; y < (int)res; y++) {
+            for (int x = 0; x < (int)res; x++) {
+                const float sc = ((float)x + 0.5f) / (float)res * 2.0f - 1.0f;
+                const float tc = ((float)y + 0.5f) / (float)res * 2.0f - 1.0f;
+                V3 o, d;
+                float tmax;
+                if (cube) {
+                    o = eye;
+                    switch (layer) {
+                        case 0: d = v3(1.0f, -tc, -sc); break;
+                        case 1: d = v3(-1.0f, -tc, sc); break;
+                        case 2: d = v3(sc, 1.0f, tc); break;
+                        case 3: d = v3(sc, -1.0f, -tc); break;
+                        case 4: d = v3(sc, -tc, 1.0f); break;
+                        default: d = v3(-sc, -tc, -1.0f); break;
+                    }
+                    tmax = 3.0e38f;
+                } else {
+                    const V4 o4 = mul(invf, V4{sc, tc, 0.0f, 1.0f});
+                    o = v3(o4.x, o4.y, o4.z);
+                    d = v3(invf[8], invf[9], invf[10]);
+                    tmax = 1.0f;
+                }
+                float best = tmax;
+                bool found = false;
+                if (!ray_is_nan(o, d) && !(d.x == 0.0f && d.y == 0.0f && d.z == 0.0f)) {
+                    const RayPre r = make_ray(o, d);
+                    for (const WTri* w : kept) {
+                        float t;
+                        if (tri_hit(r, w->p[0], w->p[1], w->p[2], 0.0f, best, &t)) {
+                            best = t;
+                            found = true;
+                        }
+                    }
+                }
+                float depth = 1.0f;
+                if (found) {
+                    const float z = cube ? (best * length(d)) / light->z_far : best;
+                    if (z < 1.0f) depth = z;
+                }
+                out[((size_t)layer * res + y) * res + x] = depth;
+            }
+        }
+    }
+    return 0;
+}
+
+void orc_bind_shadow_maps(const orc_shadow_map* maps, uint32_t n) {
+    g_shadow_maps = maps;
+    g_n_shadow_maps = n;
+}
+
+// shadowMapVolumetricLight.comp:42-74 (weight, samples, decay, density are the shader's locals :57-60)
+int orc_volumetric_shadow_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                               uint32_t width, uint32_t height, const float* depth, const uint8_t* bn, uint32_t bn_w,
+                               uint32_t bn_h, uint32_t frame, uint32_t y0, uint32_t y1, float* light_inout) {
+    const int n_lights = scene->num_lights + (int)n_extra;
+    const int frame_mod = (int)((int32_t)frame % 128);
+    const int W = (int)width, H = (int)height;
+    for (int li = 0; li < n_lights; li++)
+        if (light_at(scene, extra_lights, li).volumetric_type == 2 &&
+            ((uint32_t)li >= g_n_shadow_maps || !g_shadow_maps[li].data))
+            return -1;
+    const V3 camPos = v3(scene->cam_pos[0], scene->cam_pos[1], scene->cam_pos[2]);
+#pragma omp parallel for schedule(dynamic, 4) num_threads(orc_get_threads())
+    for (int y = (int)y0; y < (int)y1; y++) {
+        for (int x = 0; x < W; x++) {
+            const float pu = (float)x / (float)W, pv = (float)y / (float)H; // :48
+            const float pixelDepth = bilinear1(depth, W, H, pu, pv);          // :49
+            const V3 worldPos = depth_to_world(scene, pu, pv, pixelDepth);
+            const uint8_t* t = bn + 4 * ((size_t)(y % (int)bn_h) * bn_w + (size_t)(x % (int)bn_w));
+            const float bn_r = (float)t[0] / 255.0f;
+            const float noise0 = fractf(bn_r + kGoldenRatio * (float)(128 * 0 + frame_mod));
+            V3 radiance = v3(0.0f, 0.0f, 0.0f);
+            for (int li = 0; li < n_lights; li++) {
+                const luzw_light_block& light = light_at(scene, extra_lights, li);
+                if (light.volumetric_type != 2) continue; // VOLUMETRIC_TYPE_SHADOW_MAP, :54
+                const float weight = 0.000005f, decay = 1.0f, density = 1.094f;
+                const int samples = 128;
+                const V3 deltaPos = (camPos - worldPos) * density * (1.0f / (float)samples);
+                const float off = noise0 * length(deltaPos);
+                V3 samplePos = v3(camPos.x + off, camPos.y + off, camPos.z + off); // :62
+                const V3 lcol = v3(light.color[0], light.color[1], light.color[2]);
+                for (int i = 0; i < samples; i++) {
+                    samplePos = samplePos - deltaPos;
+                    const float sh = shadow_map_factor(light, g_shadow_maps[li], samplePos, samplePos); // :22-40
+                    radiance = radiance + (1.0f - sh) * lcol * light.intensity * weight * decay;     // :65
+                }
+            }
+            float* px = light_inout + 4 * ((size_t)y * W + x);
+            px[0] += radiance.x;
+            px[1] += radiance.y;
+            px[2] += radiance.z;
         }
     }
     return 0;

@@ -92,6 +92,24 @@ int orc_volumetric_screen_pass(const luzw_scene_block* scene, const luzw_light_b
                                uint32_t bn_w, uint32_t bn_h, uint32_t frame, uint32_t y0, uint32_t y1,
                                float* light_inout);
 
+/* One light's shadow map, as orc_shadow_map_pass writes it: layers * res * res floats (6 layers for a point
+ * light, else 1). */
+typedef struct orc_shadow_map {
+    const float* data;
+    uint32_t res;
+    uint32_t layers;
+} orc_shadow_map;
+/* DeferredRenderer::ShadowMapPass for one light (exhaustive, per texel).  Returns -1 for a singular viewProj[0]. */
+int orc_shadow_map_pass(const luzw_light_block* light, const orc_world* world, uint32_t res, float* out);
+/* The maps orc_light_pass (shadowType 2) and orc_volumetric_shadow_pass sample, indexed by light; the array
+ * must stay alive while they run.  NULL / 0 unbinds. */
+void orc_bind_shadow_maps(const orc_shadow_map* maps, uint32_t n);
+/* shadowMapVolumetricLight.comp main() over rows [y0, y1): adds into light_inout. */
+int orc_volumetric_shadow_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                               uint32_t width, uint32_t height, const float* depth, const uint8_t* blue_noise_rgba8,
+                               uint32_t bn_w, uint32_t bn_h, uint32_t frame, uint32_t y0, uint32_t y1,
+                               float* light_inout);
+
 /* present.frag imageType 0 -> BGRA8. */
 int orc_compose_pass(uint32_t width, uint32_t height, const float* light_in, uint8_t* out_bgra8);
 

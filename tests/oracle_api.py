@@ -30,6 +30,10 @@ class OrcGbuffer(C.Structure):
                 ("emission", C.c_void_p), ("depth", C.c_void_p)]
 
 
+class OrcShadowMap(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("res", C.c_uint32), ("layers", C.c_uint32)]
+
+
 class OrcStats(C.Structure):
     _fields_ = [("lit_pixels", C.c_uint64), ("rays", C.c_uint64), ("rays_occluded", C.c_uint64)]
 
@@ -58,6 +62,11 @@ def lib():
         L.orc_taa_pass.argtypes = [vp, u32, u32, vp, vp, vp, i32, u32, u32, vp]
         L.orc_volumetric_screen_pass.restype = i32
         L.orc_volumetric_screen_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, u32, u32, u32, u32, vp]
+        L.orc_shadow_map_pass.restype = i32
+        L.orc_shadow_map_pass.argtypes = [vp, vp, u32, vp]
+        L.orc_bind_shadow_maps.argtypes = [vp, u32]
+        L.orc_volumetric_shadow_pass.restype = i32
+        L.orc_volumetric_shadow_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, u32, u32, u32, u32, vp]
         L.orc_compose_pass.restype = i32
         L.orc_compose_pass.argtypes = [u32, u32, vp, vp]
         L.orc_gbuffer_pass.restype = i32
@@ -202,6 +211,48 @@ def volumetric_screen_pass(scene, light, depth, blue_noise, frame, extra_lights=
     bn = np.ascontiguousarray(blue_noise, np.uint8)
     n_extra = len(extra_lights) if extra_lights is not None else 0
     rc = lib().orc_volumetric_screen_pass(_p(scene), _p(extra_lights) if n_extra else None, n_extra, w, h, _p(depth),
+                                          _p(bn), bn.shape[1], bn.shape[0], frame, y0, y1, _p(out))
+    assert rc == 0
+    return out
+
+
+def shadow_map_pass(light, world, res):
+    """DeferredRenderer::ShadowMapPass for one light: [layers, res, res] float32."""
+    layers = 6 if light.type == wire.LIGHT_POINT else 1
+    out = np.zeros((layers, res, res), np.float32)
+    assert lib().orc_shadow_map_pass(_p(light), world.h, res, _p(out)) == 0
+    return out
+
+
+class BoundShadowMaps:
+    """with BoundShadowMaps({light index: map array}): orc_light_pass / volumetric_shadow_pass sample these."""
+
+    def __init__(self, maps, n_lights):
+        self.arr = (OrcShadowMap * max(n_lights, 1))()
+        self.keep = []
+        for i, m in maps.items():
+            m = np.ascontiguousarray(m, np.float32)
+            self.keep.append(m)
+            self.arr[i] = OrcShadowMap(m.ctypes.data, m.shape[1], m.shape[0])
+        self.n = n_lights
+
+    def __enter__(self):
+        lib().orc_bind_shadow_maps(_p(self.arr), self.n)
+        return self
+
+    def __exit__(self, *a):
+        lib().orc_bind_shadow_maps(None, 0)
+
+
+def volumetric_shadow_pass(scene, light, depth, blue_noise, frame, extra_lights=None, rows=None):
+    """shadowMapVolumetricLight.comp over rows (maps from BoundShadowMaps): returns a copy of `light` + shafts."""
+    h, w = depth.shape
+    y0, y1 = rows if rows else (0, h)
+    out = np.array(light, np.float32, copy=True, order="C")
+    depth = np.ascontiguousarray(depth, np.float32)
+    bn = np.ascontiguousarray(blue_noise, np.uint8)
+    n_extra = len(extra_lights) if extra_lights is not None else 0
+    rc = lib().orc_volumetric_shadow_pass(_p(scene), _p(extra_lights) if n_extra else None, n_extra, w, h, _p(depth),
                                           _p(bn), bn.shape[1], bn.shape[0], frame, y0, y1, _p(out))
     assert rc == 0
     return out

@@ -140,6 +140,47 @@ def look_at(eye, center, up=(0, 1, 0)):
     return m
 
 
+def perspective_zo(fovy_deg, aspect, near, far):
+    """glm::perspective (RH, depth 0..1, GLM_FORCE_DEPTH_ZERO_TO_ONE) without Luz's y flip, stored m[col][row]."""
+    m = perspective_vk(fovy_deg, aspect, near, far)
+    m[1][1] = -m[1][1]
+    return m
+
+
+def ortho_zo(left, right, bottom, top, near, far):
+    """glm::ortho (RH, depth 0..1), stored m[col][row]."""
+    m = np.eye(4, dtype=np.float32)
+    m[0][0] = 2.0 / (right - left)
+    m[1][1] = 2.0 / (top - bottom)
+    m[2][2] = -1.0 / (far - near)
+    m[3][0] = -(right + left) / (right - left)
+    m[3][1] = -(top + bottom) / (top - bottom)
+    m[3][2] = -near / (far - near)
+    return m
+
+
+CUBE_FACES = [((1, 0, 0), (0, -1, 0)), ((-1, 0, 0), (0, -1, 0)), ((0, 1, 0), (0, 0, 1)), ((0, -1, 0), (0, 0, -1)),
+              ((0, 0, 1), (0, -1, 0)), ((0, 0, -1), (0, -1, 0))]  # GPUScene.cpp:270-275
+
+
+def set_light_shadow_matrices(lb, centre=(0, 0, 0), half_extent=12.0, z_far=60.0):
+    """Fills light.viewProj[] / zFar like GPUScene.cpp:266-311 does: six perspective(90, 1, 0, zFar) * lookAt
+    faces for a point light; for the others one orthographic matrix looking along the light's direction (the
+    reference fits it to the camera frustum; a fixed box around `centre` exercises the same code path)."""
+    pos = np.array([lb.position[k] for k in range(3)], np.float32)
+    lb.z_far = z_far
+    if lb.type == wire.LIGHT_POINT:
+        proj = perspective_zo(90.0, 1.0, 0.0, z_far)
+        for f, (axis, up) in enumerate(CUBE_FACES):
+            set_mat(lb.view_proj[f], colmajor_mul(proj, look_at(pos, pos + np.array(axis, np.float32), up)).reshape(16))
+    else:
+        front = np.array([lb.direction[k] for k in range(3)], np.float32)
+        c = np.array(centre, np.float32)
+        view = look_at(c + front, c, (0, 1, 0))  # GPUScene.cpp:298 looks from centre + front towards the centre
+        h = half_extent
+        set_mat(lb.view_proj[0], colmajor_mul(ortho_zo(-h, h, -h, h, 3 * h, -3 * h), view).reshape(16))
+
+
 def colmajor_mul(a, b):
     """a, b stored as m[col][row]; returns a*b in the same storage."""
     return (a.T @ b.T).T.astype(np.float32)

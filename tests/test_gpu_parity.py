@@ -490,3 +490,101 @@ def test_volumetric_screen_pass_parity(rt_factory):
             shaded = np.array(strips.shaded_rows(rank, world, h))
             assert np.array_equal(d2, depth)
             assert np.array_equal(g2[shaded], ref[shaded])
+
+
+def _shadow_scene(w, h):
+    sc = S.synthetic_scene(w, h, grid=4, n_lights=3, light_samples=0, ao_samples=2, eye=(9, 4.0, 11), shadow_type=2)
+    for i in range(3):  # point, spot, directional
+        lb = sc["scene"].lights[i]
+        lb.shadow_map = 7 + i  # a bindless RID in the reference (GPUScene.cpp:329); only != -1 matters here
+        lb.num_shadow_samples = 0  # GPUScene.cpp:248: no ray-traced samples unless shadowType == RayTraced
+        S.set_light_shadow_matrices(lb)
+    return sc
+
+
+def test_shadow_map_pass_and_shadow_type_map_parity(rt_factory):
+    """luzrt_shadow_map_pass (ray-cast restatement of shadowMap.vert/.geom/.frag incl. the
+    front-face culling) against the oracle's per-triangle pipeline restatement, then light.frag's shadowType == 2
+    branch (:147-165) on the SAME maps."""
+    w, h, res = 320, 200, 96
+    sc = _shadow_scene(w, h)
+    world = O.World(sc["meshes"], sc["instances"])
+    bn = S.blue_noise()
+    rt = rt_factory()
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+    S.make_rt_scene(rt, sc)
+    rt.set_scene(sc["scene"])
+    with pytest.raises(R.LuzError):  # maps older than the scene block: loud, not stale
+        rt.light_pass(5)
+    rt.shadow_map_pass(res)
+    maps = {}
+    for i in range(3):
+        lb = sc["scene"].lights[i]
+        layers = 6 if lb.type == 0 else 1
+        got = rt.read_shadow_map(i, res, layers)
+        ref = O.shadow_map_pass(lb, world, res)
+        covered = float((ref < 1.0).mean())
+        assert covered > 0.02, (i, covered)  # the map sees geometry
+        close = np.abs(got - ref) <= 1e-5 * np.maximum(np.abs(ref), 1e-3)
+        assert float(close.mean()) >= 0.999, "light %d: %.5f of the texels agree" % (i, float(close.mean()))
+        maps[i] = got
+    assert rt.read(R.TIMINGS).shadow_map_ms > 0.0
+    # light pass with shadowType 2 on the device maps vs the oracle sampling the same maps
+    gb = O.gbuffer_pass(sc["scene"], world, sc["models"], len(sc["instances"]), sc["textures"], w, h)
+    with O.BoundShadowMaps(maps, 3):
+        rc, ref, _, am, st = O.light_pass(sc["scene"], gb, 5, bn, world, exhaustive=False, ao_words=1)
+    assert rc == 0
+    out, _, gam, gst = run_light_keep_maps(rt, sc, gb, 5)
+    assert gst.rays == st.rays and gst.lit_pixels == st.lit_pixels  # AO rays only
+    same = np.all(gam == am, axis=-1)
+    assert float(same.mean()) >= 0.999
+    # a shadow-map decision is a comparison of two close floats: allow a handful of pixels to flip
+    err = np.abs(out - ref).max(axis=-1)
+    assert float((err[same] <= RADIANCE_TOL).mean()) >= 0.999
+    lit_diff = np.abs(out - ref)[..., :3].sum()
+    assert lit_diff < 1e-3 * np.abs(ref)[..., :3].sum()
+    # shadows are really there: with shadowType 0 every light is fully shadowed (light.frag:166-168), with the
+    # maps some light arrives
+    assert float(out[..., :3].sum()) > 0.0
+
+
+def run_light_keep_maps(rt, sc, gb, frame):
+    rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
+    rt.set_debug(R.DEBUG_MASKS | R.DEBUG_STATS)
+    rt.light_pass(frame)
+    return rt.read(R.IMG_LIGHT), rt.read(R.SHADOW_MASK), rt.read(R.AO_MASK), rt.read(R.STATS)
+
+
+def test_volumetric_shadow_map_pass_parity(rt_factory):
+    """shadowMapVolumetricLight.comp through luzrt_volumetric_pass, sampling the device-rendered maps."""
+    w, h, res = 256, 160, 64
+    sc = _shadow_scene(w, h)
+    sc["scene"].shadow_type = 1  # ray-traced direct shadows, shadow-map volumetrics (GPUScene.cpp:257-264)
+    for i in range(3):
+        sc["scene"].lights[i].volumetric_type = 2
+        sc["scene"].lights[i].num_shadow_samples = 1
+    bn = S.blue_noise()
+    rt = rt_factory()
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+    S.make_rt_scene(rt, sc)
+    rt.set_scene(sc["scene"])
+    rt.set_debug(0)
+    rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+    depth = rt.read(R.GBUF_DEPTH)
+    rt.light_pass(9)
+    light = rt.read(R.IMG_LIGHT)
+    with pytest.raises(R.LuzError):
+        rt.volumetric_pass(9)  # no maps yet
+    rt.shadow_map_pass(res)
+    rt.volumetric_pass(9)
+    got = rt.read(R.IMG_LIGHT)
+    maps = {i: rt.read_shadow_map(i, res, 6 if sc["scene"].lights[i].type == 0 else 1) for i in range(3)}
+    with O.BoundShadowMaps(maps, 3):
+        ref = O.volumetric_shadow_pass(sc["scene"], light, depth, bn, 9)
+    added = ref - light
+    assert float(added[..., :3].max()) > 1e-4  # 128 steps x intensity x 5e-6
+    # each step is a shadow-map comparison; a flipped step moves a pixel by intensity * 5e-6
+    assert float(np.abs(got - ref).max()) <= 1e-4
+    assert float((np.abs(got - ref) <= 1e-6).mean()) >= 0.999
