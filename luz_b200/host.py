@@ -59,6 +59,11 @@ def load_library():
         "luzhost_halton": (C.c_float, [u32, u32]),
         "luzhost_compose_transform": (None, [fp, fp, fp, fp, fp]),
         "luzhost_mat4_inverse": (None, [fp, fp]),
+        "luzhost_perspective": (None, [C.c_float, C.c_float, C.c_float, C.c_float, fp]),
+        "luzhost_ortho": (None, [C.c_float] * 6 + [fp]),
+        "luzhost_look_at": (None, [fp, fp, fp, fp]),
+        "luzhost_mat4_mul": (None, [fp, fp, fp]),
+        "luzhost_camera_proj": (i32, [vp, C.c_float, C.c_float, fp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -224,6 +229,11 @@ class LuzHost:
         keep = [_f(center), _f(rotation)]
         self._ck(self.lib.luzhost_camera_set_orbit(self.h, *[k[0] if k else None for k in keep], zoom))
 
+    def camera_proj(self, near, far):
+        out, p = _out16()
+        self._ck(self.lib.luzhost_camera_proj(self.h, near, far, p))
+        return out
+
     def camera_use_jitter(self, on):
         self._ck(self.lib.luzhost_camera_use_jitter(self.h, 1 if on else 0))
 
@@ -237,6 +247,37 @@ def compose_transform(pos, rot, scale, parent=None):
     p, r, s = _f(pos), _f(rot), _f(scale)
     par = _f(parent) if parent is not None else None
     load_library().luzhost_compose_transform(p[0], r[0], s[0], par[0] if par else None, _f(out)[0])
+    return out
+
+
+def _out16():
+    out = np.zeros(16, np.float32)
+    return out, out.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def perspective(fovy, aspect, near, far):
+    out, p = _out16()
+    load_library().luzhost_perspective(fovy, aspect, near, far, p)
+    return out
+
+
+def ortho(left, right, bottom, top, near, far):
+    out, p = _out16()
+    load_library().luzhost_ortho(left, right, bottom, top, near, far, p)
+    return out
+
+
+def look_at(eye, center, up):
+    out, p = _out16()
+    e, c, u = _f(eye), _f(center), _f(up)
+    load_library().luzhost_look_at(e[0], c[0], u[0], p)
+    return out
+
+
+def mat4_mul(a, b):
+    out, p = _out16()
+    aa, bb = _f(a), _f(b)
+    load_library().luzhost_mat4_mul(aa[0], bb[0], p)
     return out
 
 

@@ -101,6 +101,9 @@ LUZHOST_API int luzhost_render_frame(luzhost_app* a, uint32_t flags) {
     }
     if (flags & LUZHOST_FRAME_OPAQUE)
         if ((rc = a->renderer->OpaquePass(*a->gpuScene)) != LUZRT_OK) return rtfail(a, rc);
+    // main.cpp:260-264 renders every light's map every frame; luzrt renders the ones that get sampled
+    if (a->scene->shadowType == ShadowMap || a->gpuScene->AnyShadowMapVolumetric())
+        if ((rc = a->renderer->ShadowMapPass(a->scene)) != LUZRT_OK) return rtfail(a, rc);
     LightConstants lc;
     lc.frameID = a->frameCount;
     if ((rc = a->renderer->LightPass(lc)) != LUZRT_OK) return rtfail(a, rc);
@@ -243,6 +246,33 @@ LUZHOST_API void luzhost_compose_transform(const float* pos, const float* rot, c
     const lm::mat4 m = Node::ComposeTransform(lm::vec3(pos[0], pos[1], pos[2]), lm::vec3(rot[0], rot[1], rot[2]),
                                               lm::vec3(scale[0], scale[1], scale[2]), p);
     memcpy(out16, m.data(), 64);
+}
+// glm entry points the shadow-map matrices are built from (GPUScene.cpp:266-311)
+LUZHOST_API void luzhost_perspective(float fovy, float aspect, float n, float f, float* out16) {
+    const lm::mat4 m = lm::perspective(fovy, aspect, n, f);
+    memcpy(out16, m.data(), 64);
+}
+LUZHOST_API void luzhost_ortho(float l, float r, float b, float t, float n, float f, float* out16) {
+    const lm::mat4 m = lm::ortho(l, r, b, t, n, f);
+    memcpy(out16, m.data(), 64);
+}
+LUZHOST_API void luzhost_look_at(const float* eye, const float* center, const float* up, float* out16) {
+    const lm::mat4 m = lm::look_at(lm::vec3(eye[0], eye[1], eye[2]), lm::vec3(center[0], center[1], center[2]),
+                                   lm::vec3(up[0], up[1], up[2]));
+    memcpy(out16, m.data(), 64);
+}
+LUZHOST_API void luzhost_mat4_mul(const float* a16, const float* b16, float* out16) {
+    lm::mat4 a(1.0f), b(1.0f);
+    memcpy(a.data(), a16, 64);
+    memcpy(b.data(), b16, 64);
+    const lm::mat4 m = a * b;
+    memcpy(out16, m.data(), 64);
+}
+LUZHOST_API int luzhost_camera_proj(luzhost_app* a, float n, float f, float* out16) {
+    if (!a->camera) return fail(a, -1, "no camera");
+    const lm::mat4 m = a->camera->GetProj(n, f);
+    memcpy(out16, m.data(), 64);
+    return 0;
 }
 LUZHOST_API void luzhost_mat4_inverse(const float* in16, float* out16) {
     lm::mat4 m(1.0f);

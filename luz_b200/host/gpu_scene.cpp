@@ -141,6 +141,8 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
     }
 
     anyVolumetricLight = false; // GPUScene.cpp:237
+    anyShadowMapVolumetric = false;
+    int nLights = 0;
     for (const auto& light : scene->GetAll<LightNode>(ObjectType::LightNode)) {
         luzw_light_block local{};
         luzw_light_block* block;
@@ -161,7 +163,11 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
         block->num_shadow_samples = scene->shadowType == ShadowRayTraced ? scene->lightSamples : 0;
         block->radius = light->radius;
         block->z_far = light->shadowMapFar;
-        block->shadow_map = -1; // shadow maps are outside this path
+        // the reference stores the bindless RID of the light's shadow-map image here (GPUScene.cpp:315-329), never
+        // -1 after this function; luzrt only distinguishes -1 from "has a map" and indexes maps by light
+        block->shadow_map = (int32_t)nLights;
+        ShadowViewProj(*light, *camera, view, block->view_proj);
+        nLights++;
         block->volumetric_type = light->volumetricType;
         if (light->volumetricType == LightNode::ScreenSpace) {
             block->volumetric_samples = light->volumetricScreenSamples;
@@ -173,6 +179,7 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
             block->volumetric_density = light->volumetricShadowDensity;
             block->volumetric_absorption = light->volumetricShadowAbsorption;
             anyVolumetricLight = true;
+            anyShadowMapVolumetric = true;
         }
     }
     put_vec3(s.ambient_light_color, scene->ambientLightColor);
@@ -186,6 +193,49 @@ void GPUScene::UpdateResources(const Ref<SceneAsset>& scene, const Ref<CameraNod
     s.white_texture = -1;
     s.black_texture = -1;
     s.shadow_type = scene->shadowType;
+}
+
+// light.viewProj[] as GPUScene.cpp:266-311 fills it: six perspective(90 deg, 1, 0, shadowMapFar) * lookAt cube
+// faces for a point light; for the others one orthographic matrix fitted to the part of the camera frustum
+// within farDistance / shadowMapRange, seen along the light's front vector.  Restated literally, including the
+// bounds being seeded with the first corner in WORLD space (:299-300) before the view-space corners are merged.
+void GPUScene::ShadowViewProj(const LightNode& light, const CameraNode& camera, const lm::mat4& sceneView,
+                              float (*out)[16]) {
+    using lm::vec3;
+    using lm::vec4;
+    const vec3 pos = light.GetWorldPosition();
+    if (light.lightType == LightNode::Point) {
+        const mat4 proj = lm::perspective(lm::radians(90.0f), 1.0f, 0.0f, light.shadowMapFar);
+        const vec3 axis[6] = {vec3(1, 0, 0), vec3(-1, 0, 0), vec3(0, 1, 0), vec3(0, -1, 0), vec3(0, 0, 1), vec3(0, 0, -1)};
+        const vec3 up[6] = {vec3(0, -1, 0), vec3(0, -1, 0), vec3(0, 0, 1), vec3(0, 0, -1), vec3(0, -1, 0), vec3(0, -1, 0)};
+        for (int f = 0; f < 6; f++) put_mat(out[f], proj * lm::look_at(pos, pos + axis[f], up[f]));
+        return;
+    }
+    const mat4 camProjView = lm::inverse(camera.GetProj(camera.nearDistance, camera.farDistance / light.shadowMapRange) * sceneView);
+    vec4 corners[8];
+    int n = 0;
+    for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) {
+                const vec4 pt = camProjView * vec4(2.0f * i - 1.0f, 2.0f * j - 1.0f, 2.0f * k - 1.0f, 1.0f);
+                corners[n++] = vec4(pt.x / pt.w, pt.y / pt.w, pt.z / pt.w, pt.w / pt.w);
+            }
+    vec3 centre(0.0f);
+    for (const vec4& p : corners) centre = centre + vec3(p.x, p.y, p.z);
+    centre = vec3(centre.x / 8.0f, centre.y / 8.0f, centre.z / 8.0f);
+    const float r = light.shadowMapRange;
+    const mat4 view = lm::look_at(centre + light.GetWorldFront(), centre, vec3(0.0f, 1.0f, 0.0f));
+    vec3 mn(corners[0].x, corners[0].y, corners[0].z), mx = mn;
+    auto vmin = [](float a, float b) { return b < a ? b : a; }; // glm::min(x, y) = y < x ? y : x
+    auto vmax = [](float a, float b) { return a < b ? b : a; }; // glm::max(x, y) = x < y ? y : x
+    for (const vec4& p : corners) {
+        const vec4 q = view * p;
+        mn = vec3(vmin(q.x, mn.x), vmin(q.y, mn.y), vmin(q.z, mn.z));
+        mx = vec3(vmax(q.x, mx.x), vmax(q.y, mx.y), vmax(q.z, mx.z));
+    }
+    mn.z = mn.z < 0 ? mn.z * r : mn.z / r;
+    mx.z = mx.z < 0 ? mx.z / r : mx.z * r;
+    put_mat(out[0], lm::ortho(mn.x, mx.x, mn.y, mx.y, mx.z, mn.z) * view);
 }
 
 int GPUScene::UpdateResourcesGPU(int tlasMode) {
@@ -204,6 +254,7 @@ int DeferredRenderer::OpaquePass(GPUScene& g) {
     return luzrt_gbuffer_pass(rt, g.modelsBlock.empty() ? nullptr : g.modelsBlock.data(), (uint32_t)g.modelsBlock.size());
 }
 int DeferredRenderer::LightPass(LightConstants c) { return luzrt_light_pass(rt, (uint32_t)c.frameID); }
+int DeferredRenderer::ShadowMapPass(const Ref<SceneAsset>& scene) { return luzrt_shadow_map_pass(rt, scene->shadowResolution); }
 int DeferredRenderer::ScreenSpaceVolumetricLightPass(GPUScene&, int frame) { return luzrt_volumetric_pass(rt, (uint32_t)frame); }
 int DeferredRenderer::TAAPass(GPUScene&, const Ref<SceneAsset>& scene) {
     if (!scene->taaEnabled) return LUZRT_OK; // DeferredRenderer.cpp:426

@@ -52,8 +52,12 @@ struct GPUScene {
     std::vector<luzrt_instance> instances;
     std::unordered_map<UUID, GPUMesh> meshes;
     std::unordered_map<UUID, GPUTexture> textures;
+    static void ShadowViewProj(const LightNode& light, const CameraNode& camera, const lm::mat4& sceneView,
+                               float (*out)[16]); // GPUScene.cpp:266-311
     bool anyVolumetricLight = false; // GPUScene.cpp:16, :403-405
     bool AnyVolumetricLight() const { return anyVolumetricLight; }
+    bool anyShadowMapVolumetric = false;
+    bool AnyShadowMapVolumetric() const { return anyShadowMapVolumetric; }
     bool firstFrame = true;
     int32_t nextCpuRid = 0;
 };
@@ -67,7 +71,8 @@ struct DeferredRenderer {
     int CreateImages(uint32_t width, uint32_t height);                      // DeferredRenderer.cpp:175-248
     int OpaquePass(GPUScene& gpuScene);                                     // main.cpp:242-258 (G-buffer)
     int LightPass(LightConstants constants);                                // DeferredRenderer.cpp:324-345
-    int ScreenSpaceVolumetricLightPass(GPUScene& gpuScene, int frame);      // :294-307
+    int ShadowMapPass(const Ref<SceneAsset>& scene);                        // :268-291, for every light (main.cpp:260-264)
+    int ScreenSpaceVolumetricLightPass(GPUScene& gpuScene, int frame);      // :294-307 (+ :309-322)
     int TAAPass(GPUScene& gpuScene, const Ref<SceneAsset>& scene);          // :425-445
     int ComposePass(const Ref<SceneAsset>& scene);                          // :347-370
     int SwapLightHistory();                                                 // :469-471

@@ -1268,6 +1268,12 @@ int orc_shadow_map_pass(const luzw_light_block* light, const orc_world* world, u
     return 0;
 }
 
+float orc_shadow_factor(const luzw_light_block* light, const orc_shadow_map* map, const float* frag_pos,
+                        const float* shadow_origin) {
+    return shadow_map_factor(*light, *map, v3(frag_pos[0], frag_pos[1], frag_pos[2]),
+                             v3(shadow_origin[0], shadow_origin[1], shadow_origin[2]));
+}
+
 void orc_bind_shadow_maps(const orc_shadow_map* maps, uint32_t n) {
     g_shadow_maps = maps;
     g_n_shadow_maps = n;

@@ -74,7 +74,8 @@ void orc_trace_closest(const orc_world* w, uint32_t n, const float* origins3, co
                        const float* tmax, int exhaustive, float* t, int32_t* inst, int32_t* prim);
 
 /* light.frag main() over rows [y0, y1).  out_rgba32f is the full W*H*4 image (only the rows
- * are written).  Masks may be NULL.  Returns 0, or -1 for the out-of-scope shadow-map branch. */
+ * are written).  Masks may be NULL.  Returns 0, or -1 if shadowType == 2 and a light's map is not bound
+ * (orc_bind_shadow_maps). */
 int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
                    uint32_t width, uint32_t height, const orc_gbuffer* gb, uint32_t frame,
                    const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
@@ -101,6 +102,9 @@ typedef struct orc_shadow_map {
 } orc_shadow_map;
 /* DeferredRenderer::ShadowMapPass for one light (exhaustive, per texel).  Returns -1 for a singular viewProj[0]. */
 int orc_shadow_map_pass(const luzw_light_block* light, const orc_world* world, uint32_t res, float* out);
+/* The SHADOW_TYPE_MAP branch of EvaluateShadow (light.frag:147-165) for one point: 1 = in shadow. */
+float orc_shadow_factor(const luzw_light_block* light, const orc_shadow_map* map, const float* frag_pos,
+                        const float* shadow_origin);
 /* The maps orc_light_pass (shadowType 2) and orc_volumetric_shadow_pass sample, indexed by light; the array
  * must stay alive while they run.  NULL / 0 unbinds. */
 void orc_bind_shadow_maps(const orc_shadow_map* maps, uint32_t n);

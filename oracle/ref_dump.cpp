@@ -198,7 +198,39 @@ int main(int argc, char** argv) {
             printf("}");
         }
     }
-    printf("]}\n");
+    printf("],");
+
+    // ---- the glm / camera entry points GPUScene.cpp:266-311 builds light.viewProj[] from, called on seeded
+    //      inputs: perspective(90 deg, 1, 0, far) (zNear = 0), lookAt with the six cube-face axes / ups, ortho with
+    //      zNear > zFar, CameraNode::GetProj(near, far / range), inverse and products of those ------------------
+    printf("\"shadowGlm\":{");
+    {
+        put_mat("persp90_far2000", glm::perspective(glm::radians(90.0f), 1.0f, 0.0f, 2000.0f));
+        put_mat("persp90_far37", glm::perspective(glm::radians(90.0f), 1.0f, 0.0f, 37.5f));
+        const glm::vec3 pos(3.139984130859375f, 6.1400675773620605f, -3.6627626419067383f);
+        put_floats("pos", &pos.x, 3);
+        const glm::vec3 axis[6] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
+        const glm::vec3 up[6] = {{0, -1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}, {0, -1, 0}, {0, -1, 0}};
+        printf("\"faces\":[");
+        for (int f = 0; f < 6; f++) {
+            glm::mat4 v = glm::lookAt(pos, pos + axis[f], up[f]);
+            glm::mat4 vp = glm::perspective(glm::radians(90.0f), 1.0f, 0.0f, 2000.0f) * v;
+            printf("%s{", f ? "," : "");
+            put_mat("lookAt", v);
+            put_mat("viewProj", vp, false);
+            printf("}");
+        }
+        printf("],");
+        put_mat("ortho", glm::ortho(-3.25f, 5.5f, -2.125f, 7.75f, 11.5f, -9.25f));
+        glm::mat4 cp = camera->GetProj(camera->nearDistance, camera->farDistance / 3.0f);
+        put_mat("camProj_far_over_3", cp);
+        glm::mat4 cv = camera->GetView();
+        put_mat("camView", cv);
+        put_mat("inverse_camProjView", glm::inverse(cp * cv));
+        const glm::vec3 centre(0.5f, -1.25f, 2.0f), front(0.3f, -1.0f, 0.2f);
+        put_mat("lookAt_front", glm::lookAt(centre + front, centre, glm::vec3(.0f, 1.0f, .0f)), false);
+    }
+    printf("}}\n");
     fclose(g_out);
     return 0;
 }

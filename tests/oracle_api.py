@@ -65,6 +65,8 @@ def lib():
         L.orc_shadow_map_pass.restype = i32
         L.orc_shadow_map_pass.argtypes = [vp, vp, u32, vp]
         L.orc_bind_shadow_maps.argtypes = [vp, u32]
+        L.orc_shadow_factor.restype = C.c_float
+        L.orc_shadow_factor.argtypes = [vp, vp, vp, vp]
         L.orc_volumetric_shadow_pass.restype = i32
         L.orc_volumetric_shadow_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp, u32, u32, u32, u32, u32, vp]
         L.orc_compose_pass.restype = i32
@@ -222,6 +224,14 @@ def shadow_map_pass(light, world, res):
     out = np.zeros((layers, res, res), np.float32)
     assert lib().orc_shadow_map_pass(_p(light), world.h, res, _p(out)) == 0
     return out
+
+
+def shadow_factor(light, shadow_map, frag_pos, shadow_origin=None):
+    m = np.ascontiguousarray(shadow_map, np.float32)
+    rec = OrcShadowMap(m.ctypes.data, m.shape[1], m.shape[0])
+    fp = np.asarray(frag_pos, np.float32)
+    so = np.asarray(shadow_origin if shadow_origin is not None else frag_pos, np.float32)
+    return float(lib().orc_shadow_factor(_p(light), _p(rec), _p(fp), _p(so)))
 
 
 class BoundShadowMaps:

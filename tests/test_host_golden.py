@@ -139,7 +139,7 @@ def test_scene_block_sequence_matches_reference_camera(project, g):
             assert np.array_equal(f32(lb.direction[:]), f32(l["direction"]))
             assert np.array_equal(f32([lb.inner_angle, lb.outer_angle]), f32(l["inner_outer_radians"]))
             assert np.array_equal(f32([lb.intensity, lb.radius, lb.z_far]), f32(l["intensity_radius_zfar"]))
-            assert lb.type == l["type"] and lb.num_shadow_samples == 1 and lb.shadow_map == -1
+            assert lb.type == l["type"] and lb.num_shadow_samples == 1 and lb.shadow_map == i  # 'has a map' (GPUScene.cpp:329)
         assert sb.ao_num_samples == 1 and sb.shadow_type == 1
     # jitter is a 16-cycle of Halton(2,3)
     assert frames[0]["jitter"] == frames[16]["jitter"] and frames[1]["jitter"] != frames[0]["jitter"]
@@ -201,3 +201,118 @@ def test_loader_errors(tmp_path):
     (tmp_path / "oob.luzbin").write_bytes(b"\0" * 16)
     with pytest.raises(H.HostError):
         app.load_project(str(tmp_path / "oob.luz"), str(tmp_path / "oob.luzbin"))
+
+
+def test_shadow_matrix_primitives_match_glm(project, g):
+    """The glm / camera calls GPUScene.cpp:266-311 builds light.viewProj[] from, against the reference's own glm
+    (oracle/ref_dump.cpp 'shadowGlm'): perspective with zNear = 0, lookAt with the cube-face ups, ortho with
+    zNear > zFar, CameraNode::GetProj(near, far / range), products and the inverse."""
+    sg = g["shadowGlm"]
+    rad90 = float(np.float32(90.0) * np.float32(0.01745329251994329576923690768489))
+    assert np.array_equal(H.perspective(rad90, 1.0, 0.0, 2000.0), f32(sg["persp90_far2000"]))
+    assert np.array_equal(H.perspective(rad90, 1.0, 0.0, 37.5), f32(sg["persp90_far37"]))
+    pos = f32(sg["pos"])
+    for f, (axis, up) in enumerate(S.CUBE_FACES):
+        v = H.look_at(pos, pos + f32(axis), up)
+        assert np.array_equal(v, f32(sg["faces"][f]["lookAt"])), f
+        assert np.array_equal(H.mat4_mul(sg["persp90_far2000"], v), f32(sg["faces"][f]["viewProj"])), f
+    assert np.array_equal(H.ortho(-3.25, 5.5, -2.125, 7.75, 11.5, -9.25), f32(sg["ortho"]))
+    app = H.LuzHost(None)
+    app.load_project(*project)
+    app.set_extent(1280, 720, create_images=False)
+    near, far = g["camera"]["zoom_far_near_fov_w_h"][2], g["camera"]["zoom_far_near_fov_w_h"][1]
+    cp = app.camera_proj(near, float(np.float32(far) / np.float32(3.0)))
+    assert np.array_equal(cp, f32(sg["camProj_far_over_3"]))
+    inv = H.mat4_inverse(H.mat4_mul(sg["camProj_far_over_3"], sg["camView"]))
+    ref = f32(sg["inverse_camProjView"])
+    assert np.array_equal(inv, ref) or np.allclose(inv, ref, rtol=3e-6, atol=1e-9)
+    c, fr = f32([0.5, -1.25, 2.0]), f32([0.3, -1.0, 0.2])
+    assert np.array_equal(H.look_at(c + fr, c, (0, 1, 0)), f32(sg["lookAt_front"]))
+
+
+def test_light_view_proj_like_gpuscene_266_311(project, g):
+    """LightBlock.viewProj[] of the host mirror: the default project's point light gets exactly the six cube-face
+    matrices glm produces; a directional light gets the frustum-fitted orthographic matrix, checked against an
+    independent float64 evaluation of GPUScene.cpp:278-310."""
+    app = H.LuzHost(None)
+    app.load_project(*project)
+    app.set_extent(1280, 720, create_images=False)
+    app.update_resources()
+    sb = app.scene_block()
+    lb = sb.lights[0]
+    assert lb.type == wire.LIGHT_POINT and lb.shadow_map != -1 and lb.z_far == 2000.0
+    assert np.array_equal(f32(lb.position[:]), f32(g["shadowGlm"]["pos"]))
+    for f in range(6):
+        assert np.array_equal(f32(lb.view_proj[f][:]), f32(g["shadowGlm"]["faces"][f]["viewProj"])), f
+    # the six matrices map a direction to the (sc, tc) / |ma| of the Vulkan cube-face table (the property
+    # luzrt_shadow_map_pass relies on for its texel-centre rays)
+    rng = np.random.default_rng(3)
+    pos = np.array(lb.position[:], np.float64)
+    for f in range(6):
+        vp = np.array(lb.view_proj[f][:], np.float64).reshape(4, 4).T
+        for _ in range(50):
+            sc, tc = rng.uniform(-1, 1, 2)
+            d = [(1, -tc, -sc), (-1, -tc, sc), (sc, 1, tc), (sc, -1, -tc), (sc, -tc, 1), (-sc, -tc, -1)][f]
+            c = vp @ np.array([*(pos + 5.0 * np.array(d)), 1.0])
+            assert c[3] > 0 and abs(c[0] / c[3] - sc) < 1e-5 and abs(c[1] / c[3] - tc) < 1e-5
+            assert abs(c[2] / c[3] - 1.0) < 1e-6  # zNear = 0: every fragment sits at depth 1, hence shadowMap.frag:15
+
+
+def _expected_ortho_view_proj(cam_proj, view, front, rng_r):
+    inv = np.linalg.inv(cam_proj @ view)
+    corners = []
+    for i in range(2):
+        for j in range(2):
+            for k in range(2):
+                p = inv @ np.array([2.0 * i - 1, 2.0 * j - 1, 2.0 * k - 1, 1.0])
+                corners.append(p / p[3])
+    centre = np.mean([c[:3] for c in corners], axis=0)
+    eye, up = centre + front, np.array([0.0, 1.0, 0.0])
+    fwd = (centre - eye) / np.linalg.norm(centre - eye)
+    s = np.cross(fwd, up)
+    s /= np.linalg.norm(s)
+    u = np.cross(s, fwd)
+    lv = np.eye(4)
+    lv[0, :3], lv[1, :3], lv[2, :3] = s, u, -fwd
+    lv[:3, 3] = [-s @ eye, -u @ eye, fwd @ eye]
+    mn = corners[0][:3].copy()  # seeded in world space (GPUScene.cpp:299-300)
+    mx = mn.copy()
+    for c in corners:
+        q = (lv @ c)[:3]
+        mn, mx = np.minimum(q, mn), np.maximum(q, mx)
+    mn[2] = mn[2] * rng_r if mn[2] < 0 else mn[2] / rng_r
+    mx[2] = mx[2] / rng_r if mx[2] < 0 else mx[2] * rng_r
+    l, r_, b, t, n, f = mn[0], mx[0], mn[1], mx[1], mx[2], mn[2]
+    o = np.eye(4)
+    o[0, 0], o[1, 1], o[2, 2] = 2 / (r_ - l), 2 / (t - b), -1 / (f - n)
+    o[0, 3], o[1, 3], o[2, 3] = -(r_ + l) / (r_ - l), -(t + b) / (t - b), -n / (f - n)
+    return o @ lv
+
+
+def test_directional_light_view_proj(project, g, tmp_path):
+    import json as J
+    with open(project[0]) as f:
+        doc = J.load(f)
+    for sc in doc["scenes"].values():
+        for n in sc["nodes"]:
+            if n.get("type") == 7:
+                n["lightType"] = 2
+                n["rotation"] = [25.0, 40.0, 10.0]
+                n["shadowMapRange"] = 3.0
+    path = tmp_path / "dir.luz"
+    path.write_text(J.dumps(doc))
+    app = H.LuzHost(None)
+    app.load_project(str(path), project[1])
+    app.set_extent(1280, 720, create_images=False)
+    app.camera_use_jitter(False)
+    app.update_resources()
+    sb = app.scene_block()
+    lb = sb.lights[0]
+    assert lb.type == wire.LIGHT_DIRECTIONAL
+    got = np.array(lb.view_proj[0][:], np.float64).reshape(4, 4).T
+    near, far = g["camera"]["zoom_far_near_fov_w_h"][2], g["camera"]["zoom_far_near_fov_w_h"][1]
+    cam_proj = np.array(app.camera_proj(near, float(np.float32(far) / np.float32(3.0))), np.float64).reshape(4, 4).T
+    view = np.array(sb.view[:], np.float64).reshape(4, 4).T
+    exp = _expected_ortho_view_proj(cam_proj, view, np.array(lb.direction[:], np.float64), 3.0)
+    assert got[3].tolist() == [0.0, 0.0, 0.0, 1.0]  # orthographic: what luzrt_shadow_map_pass requires
+    assert np.allclose(got, exp, rtol=2e-3, atol=2e-4), (got, exp)

@@ -344,3 +344,110 @@ def test_volumetric_screen_pass_known_answers():
     for (x, y) in [(0, 0), (63, 47), (31, 5), (10, 30), (50, 20), (5, 44)]:
         exp = _numpy_volumetric_pixel(sc["scene"], gb.depth, bn, x, y, 77)
         assert [float(v) for v in out[y, x, :3]] == [float(v) for v in exp], (x, y)
+
+
+def _quad(flip=False):
+    """Unit-ish quad [-1, 1]^2 at y = 0; counter-clockwise seen from +y (normal +y) unless flipped."""
+    v = np.zeros((4, 12), np.float32)
+    v[:, :3] = [(-1, 0, -1), (-1, 0, 1), (1, 0, 1), (1, 0, -1)]
+    idx = np.array([0, 1, 2, 0, 2, 3], np.uint32)
+    if flip:
+        idx = idx.reshape(2, 3)[:, ::-1].reshape(-1).copy()
+    return v, idx
+
+
+def test_shadow_map_pass_known_answers():
+    """DeferredRenderer::ShadowMapPass restated (shadowMap.geom/.frag): closed-form cube map of a quad under a
+    point light, the front-face culling (`.cullFront = true`; light.viewProj has no y flip, so for a point light the
+    faces turned TOWARDS the light are the ones rendered), and an orthographic map checked by un-projecting every
+    texel."""
+    res = 32
+    ident = np.eye(4, dtype=np.float32).reshape(16)
+    lb = wire.LightBlock()
+    lb.type = wire.LIGHT_POINT
+    lb.position[0], lb.position[1], lb.position[2] = 0.0, 2.0, 0.0
+    S.set_light_shadow_matrices(lb, z_far=10.0)
+    up = O.World([_quad()], [(0, ident, 0)])
+    m = O.shadow_map_pass(lb, up, res)
+    c = (np.arange(res, dtype=np.float64) + 0.5) / res * 2 - 1
+    sc, tc = np.meshgrid(c, c)  # [row = tc, col = sc]
+    # layer 3 (-Y): direction (sc, -1, -tc) meets y = 0 at t = 2, i.e. at (2 sc, 0, -2 tc): inside iff |sc|, |tc| <= 1/2
+    inside = (np.abs(sc) < 0.5) & (np.abs(tc) < 0.5)
+    exp = np.where(inside, 2.0 * np.sqrt(1 + sc * sc + tc * tc) / 10.0, 1.0)
+    assert np.allclose(m[3], exp, rtol=0, atol=2e-6)
+    assert inside.sum() == 256 and abs(float(m[3][res // 2, res // 2]) - 0.2) < 1e-3
+    for layer in (0, 1, 2, 4, 5):
+        assert np.all(m[layer] == 1.0), layer  # the clear value everywhere else
+    # the same quad wound the other way faces away from the light: front-facing in the light's framebuffer, culled
+    down = O.World([_quad(flip=True)], [(0, ident, 0)])
+    assert np.all(O.shadow_map_pass(lb, down, res) == 1.0)
+    # ... and a mirrored instance (det < 0) flips the facing back
+    mirror = np.diag([1.0, 1.0, -1.0, 1.0]).astype(np.float32).reshape(16)
+    assert np.allclose(O.shadow_map_pass(lb, O.World([_quad(flip=True)], [(0, mirror, 0)]), res)[3], exp, atol=2e-6)
+    # zFar closer than the quad: LESS against the cleared 1.0 keeps the clear value
+    lb.z_far = 1.5
+    assert np.all(O.shadow_map_pass(lb, up, res) == 1.0)
+
+    # orthographic (spot / directional): un-project each texel with its stored depth
+    ol = wire.LightBlock()
+    ol.type = wire.LIGHT_DIRECTIONAL
+    ol.direction[0], ol.direction[1], ol.direction[2] = 0.3, -1.0, 0.2
+    S.set_light_shadow_matrices(ol, centre=(0.2, 0.0, -0.1), half_extent=2.0)
+    # GPUScene.cpp:298-309 looks from centre + front back towards the centre and hands glm::ortho zNear = max.z,
+    # zFar = min.z: depth still grows along the light, but x is mirrored, so here `.cullFront` drops the faces
+    # turned TOWARDS the light and the map holds the faces turned away from it (the classic back-face shadow map)
+    assert np.all(O.shadow_map_pass(ol, up, res) == 1.0)
+    om = O.shadow_map_pass(ol, down, res)[0]
+    assert 0.1 < float((om < 1.0).mean()) < 0.9
+    vp = np.array(ol.view_proj[0][:], np.float64).reshape(4, 4).T
+    inv = np.linalg.inv(vp)
+    for y in range(res):
+        for x in range(res):
+            a = inv @ np.array([c[x], c[y], 0.0, 1.0])
+            b = inv @ np.array([c[x], c[y], 1.0, 1.0])
+            t = a[1] / (a[1] - b[1])  # where the texel's line meets the plane y = 0
+            hit = a + t * (b - a)
+            on_quad = 0.0 < t < 1.0 and abs(hit[0]) < 1.0 and abs(hit[2]) < 1.0
+            edge = min(abs(abs(hit[0]) - 1.0), abs(abs(hit[2]) - 1.0)) < 1e-3
+            if edge:
+                continue
+            if on_quad:
+                assert abs(float(om[y, x]) - t) < 1e-5, (x, y)
+            else:
+                assert om[y, x] == 1.0, (x, y)
+
+
+def test_shadow_map_lookup_known_answers():
+    """light.frag:147-165: cube face selection by the Vulkan rules, the 0.05 bias and zFar scaling of the point
+    branch, the un-divided orthographic branch with `>=`, bilinear taps and REPEAT wrap."""
+    res = 8
+    lb = wire.LightBlock()
+    lb.type = wire.LIGHT_POINT
+    lb.z_far = 10.0
+    cube = np.stack([np.full((res, res), 0.1 * (f + 1), np.float32) for f in range(6)])
+    # value v on a face means occluder distance 10 v: a point at distance d is shadowed iff d - 0.05 >= 10 v
+    for d, face in (((1, 0.2, -0.3), 0), ((-1, 0.2, 0.3), 1), ((0.2, 1, 0.3), 2), ((0.2, -1, 0.3), 3),
+                    ((0.2, 0.3, 1), 4), ((0.2, 0.3, -1), 5), ((1, 1, 1), 4), ((1, 1, 0.5), 2), ((1, -1, -1), 5)):
+        dv = np.array(d, np.float64) / np.linalg.norm(d)
+        occl = 10.0 * 0.1 * (face + 1)
+        assert O.shadow_factor(lb, cube, dv * (occl + 0.06)) == 1.0, (d, face)
+        assert O.shadow_factor(lb, cube, dv * (occl + 0.04)) == 0.0, (d, face)
+    # 2-D: viewProj = identity => uv = xy * 0.5 + 0.5, compared value = z (no divide by w, :157-159)
+    ol = wire.LightBlock()
+    ol.type = wire.LIGHT_SPOT
+    S.set_mat(ol.view_proj[0], np.eye(4, dtype=np.float32).reshape(16))
+    ramp = np.tile((np.arange(res, dtype=np.float32) + 0.5) / res, (res, 1))[None]  # texel value = its u
+    u_to_x = lambda u: 2.0 * u - 1.0
+    for u in (0.0625, 0.3, 0.5, 0.77):  # inside the first / last texel centre the tap is linear in u
+        x = u_to_x(u)
+        assert O.shadow_factor(ol, ramp, (x, 0.1, u + 1e-4)) == 1.0 and O.shadow_factor(ol, ramp, (x, 0.1, u - 1e-4)) == 0.0
+    # REPEAT: u = 1.3 samples the same texels as u = 0.3; across the border the tap blends last and first column
+    assert O.shadow_factor(ol, ramp, (u_to_x(1.3), 0.0, 0.3 + 1e-4)) == 1.0
+    assert O.shadow_factor(ol, ramp, (u_to_x(1.3), 0.0, 0.3 - 1e-4)) == 0.0
+    wrap = 0.5 * (ramp[0, 0, 0] + ramp[0, 0, -1])  # u = 1.0: halfway between the last and the first texel centre
+    assert O.shadow_factor(ol, ramp, (u_to_x(1.0), 0.0, wrap + 1e-4)) == 1.0
+    assert O.shadow_factor(ol, ramp, (u_to_x(1.0), 0.0, wrap - 1e-4)) == 0.0
+    # `>=`: equality is shadowed; the shadow ORIGIN (not fragPos) is what gets projected (:157)
+    const = np.full((1, res, res), 0.25, np.float32)
+    assert O.shadow_factor(ol, const, (0.0, 0.0, 0.9), shadow_origin=(0.0, 0.0, 0.25)) == 1.0
+    assert O.shadow_factor(ol, const, (0.0, 0.0, 0.9), shadow_origin=(0.0, 0.0, 0.2499)) == 0.0
