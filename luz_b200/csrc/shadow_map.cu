@@ -27,8 +27,10 @@ namespace luz {
 namespace {
 
 __global__ void __launch_bounds__(128) k_shadow_map(const ShadowMapArgs a) {
-    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const uint32_t y = blockIdx.y * 4 + (threadIdx.x >> 5);
+    // one warp = 8 x 4 texels (neighbouring rays stay together), one CTA = 16 x 8
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const uint32_t y = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const uint32_t layer = blockIdx.z;
     if (x >= a.res || y >= a.res) return;
     const float sc = ((float)x + 0.5f) / (float)a.res * 2.0f - 1.0f;
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(128) k_shadow_map(const ShadowMapArgs a) {
 
 cudaError_t launch_shadow_map(cudaStream_t stream, const ShadowMapArgs& args) {
     if (args.res == 0 || args.layers == 0) return cudaSuccess;
-    const dim3 grid((args.res + 31) / 32, (args.res + 3) / 4, args.layers);
+    const dim3 grid((args.res + 15) / 16, (args.res + 7) / 8, args.layers);
     k_shadow_map<<<grid, 128, 0, stream>>>(args);
     return cudaGetLastError();
 }
