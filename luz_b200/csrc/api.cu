@@ -84,6 +84,15 @@ struct luzrt_ctx {
     cudaStream_t upload_stream = nullptr, download_stream = nullptr;
     cudaEvent_t ev_flip = nullptr, ev_uploaded = nullptr, ev_result = nullptr, ev_downloaded = nullptr;
     bool upload_pending = false, download_pending = false;
+    const void* download_src = nullptr; // light image the asynchronous read-back in flight is reading
+    // Page-locked staging ring for the small per-frame uploads (light records ...): a cudaMemcpyAsync from pageable
+    // memory first synchronises the stream, which would stall the host behind the previous frame every frame.
+    struct Staging {
+        void* host = nullptr;
+        size_t cap = 0;
+        cudaEvent_t done = nullptr;
+    } staging[4];
+    uint32_t staging_next = 0;
     bool history_valid = false;
 
     uchar4* blue_noise = nullptr;
@@ -207,12 +216,42 @@ int grow(luzrt_ctx* c, T*& p, size_t& cap, size_t need) {
     return LUZRT_OK;
 }
 
+// stream-ordered upload of a small host array through the page-locked staging ring
+int stage_upload(luzrt_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return LUZRT_OK;
+    luzrt_ctx::Staging& s = c->staging[c->staging_next++ % 4];
+    if (!s.done)
+        CU(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    else
+        CU(c, cudaEventSynchronize(s.done)); // four uploads ago: long finished
+    if (s.cap < bytes) {
+        if (s.host) cudaFreeHost(s.host);
+        s.host = nullptr;
+        s.cap = 0;
+        if (cudaHostAlloc(&s.host, bytes + bytes / 2 + 256, cudaHostAllocDefault) != cudaSuccess)
+            return fail(c, LUZRT_E_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        s.cap = bytes + bytes / 2 + 256;
+    }
+    memcpy(s.host, src, bytes);
+    CU(c, cudaMemcpyAsync(dst, s.host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(s.done, c->stream));
+    return LUZRT_OK;
+}
+
 // makes the ctx stream wait for the in-flight gather if it targets one of the given buffers (nullptr = any)
 cudaError_t wait_gather(luzrt_ctx* c, const void* a = nullptr, const void* b = nullptr, const void* d = nullptr) {
     if (!c->gather_buf) return cudaSuccess;
     if (a && c->gather_buf != a && c->gather_buf != b && c->gather_buf != d) return cudaSuccess;
     c->gather_buf = nullptr;
     return cudaStreamWaitEvent(c->stream, c->ev_gathered, 0);
+}
+
+// Makes the ctx stream wait for the asynchronous read-back in flight if it reads the image about to be WRITTEN.
+// (After SwapLightHistory the image being read back is lightHistory, which the next frame only reads: its light
+// pass and TAA then overlap the download instead of queueing behind it.)
+cudaError_t wait_download(luzrt_ctx* c, const void* written) {
+    if (!c->download_pending || c->download_src != written) return cudaSuccess;
+    return cudaStreamWaitEvent(c->stream, c->ev_downloaded, 0);
 }
 
 void ev_begin(luzrt_ctx* c, int which) { cudaEventRecord(c->ev[which][0], c->stream); }
@@ -334,6 +373,10 @@ void luzrt_destroy(luzrt_ctx* c) {
             cudaStreamSynchronize(st);
             cudaStreamDestroy(st);
         }
+    for (auto& st : c->staging) {
+        if (st.done) cudaEventDestroy(st.done);
+        if (st.host) cudaFreeHost(st.host);
+    }
     for (cudaEvent_t e : {c->ev_flip, c->ev_uploaded, c->ev_result, c->ev_downloaded})
         if (e) cudaEventDestroy(e);
     if (c->ev_resolved) cudaEventDestroy(c->ev_resolved);
@@ -705,10 +748,10 @@ int luzrt_set_scene(luzrt_ctx* c, const luzw_scene_block* s, const luzw_light_bl
     }
     if (!vols.empty()) {
         if ((rc = grow(c, c->d_vol_lights, c->vol_lights_cap, vols.size())) != LUZRT_OK) return rc;
-        CU(c, cudaMemcpyAsync(c->d_vol_lights, vols.data(), vols.size() * sizeof(VolLight), cudaMemcpyHostToDevice, c->stream));
+        if ((rc = stage_upload(c, c->d_vol_lights, vols.data(), vols.size() * sizeof(VolLight))) != LUZRT_OK) return rc;
     }
     if ((rc = grow(c, c->d_lights, c->lights_cap, recs.size())) != LUZRT_OK) return rc;
-    CU(c, cudaMemcpyAsync(c->d_lights, recs.data(), recs.size() * sizeof(LightRec), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = stage_upload(c, c->d_lights, recs.data(), recs.size() * sizeof(LightRec))) != LUZRT_OK) return rc;
     FrameConst& fc = c->fc;
     memcpy(fc.inverse_proj, s->inverse_proj, 64);
     memcpy(fc.inverse_view, s->inverse_view, 64);
@@ -856,6 +899,7 @@ int luzrt_read_owned_async(luzrt_ctx* c, int which, void* dst, size_t bytes) {
                           c->download_stream));
     CU(c, cudaEventRecord(c->ev_downloaded, c->download_stream));
     c->download_pending = true;
+    c->download_src = src;
     return LUZRT_OK;
 }
 
@@ -989,7 +1033,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
     CU(c, wait_gather(c, a.out));
-    if (c->download_pending) CU(c, cudaStreamWaitEvent(c->stream, c->ev_downloaded, 0)); // the image may be reused
+    CU(c, wait_download(c, a.out));
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
@@ -1093,8 +1137,9 @@ int luzrt_shadow_map_pass(luzrt_ctx* c, uint32_t resolution) {
     }
     int rc;
     if ((rc = grow(c, c->d_shadow_recs, c->shadow_recs_cap, c->host_shadow_recs.size())) != LUZRT_OK) return rc;
-    CU(c, cudaMemcpyAsync(c->d_shadow_recs, c->host_shadow_recs.data(), c->host_shadow_recs.size() * sizeof(ShadowMapRec),
-                          cudaMemcpyHostToDevice, c->stream));
+    if ((rc = stage_upload(c, c->d_shadow_recs, c->host_shadow_recs.data(),
+                           c->host_shadow_recs.size() * sizeof(ShadowMapRec))) != LUZRT_OK)
+        return rc;
     ev_end(c, EV_SHADOWMAP);
     c->shadow_maps_current = true;
     return LUZRT_OK;
@@ -1135,6 +1180,7 @@ int luzrt_volumetric_pass(luzrt_ctx* c, uint32_t frame) {
     a.light = c->lightA;
     a.rows = shade_bands(c);
     CU(c, wait_gather(c, a.light));
+    CU(c, wait_download(c, a.light));
     ev_begin(c, EV_VOLUMETRIC);
     a.shadow_maps = c->d_shadow_recs;
     bool any_screen = false;
@@ -1167,6 +1213,7 @@ int luzrt_taa_pass(luzrt_ctx* c, int reconstruct) {
     a.rows = own_bands(c);
     a.reconstruct = reconstruct ? 1 : 0;
     CU(c, wait_gather(c, a.light_in, a.history, a.out));
+    CU(c, wait_download(c, a.out));
     ev_begin(c, EV_TAA);
     CU(c, launch_taa_pass(c->stream, a));
     c->launches++;

@@ -411,25 +411,46 @@ def test_pipelined_host_path_matches_blocking_calls(rt_factory):
         rt.swap_light_history()
         ref_frames.append(out)
 
-    rt = setup()
     pinned = [[torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in
                (gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)] for _, gb in gbs]
-    outs = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in gbs]
-    rt.prefetch_gbuffer(*[t.numpy() for t in pinned[0]])
-    for i, (s2, gb) in enumerate(gbs):
-        rt.set_scene(s2["scene"])
-        rt.flip_gbuffer()
-        rt.light_pass(i)
-        rt.taa_pass(True)
+    # "late": upload i+1 is enqueued after step i's read-back call; "early": right after the flip, so that it runs
+    # while step i is shaded (the order bench.py's e2e uses).  Several rounds over the inputs rotate the three light
+    # images and the two G-buffer sets through every role while copies are in flight.
+    for order in ("late", "early"):
+        rt = setup()
+        n = 3 * len(gbs)
+        outs = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(n)]
+        seq_ref = []
+        rt_ref = setup()
+        for i in range(n):
+            s2, gb = gbs[i % len(gbs)]
+            rt_ref.set_scene(s2["scene"])
+            rt_ref.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
+            rt_ref.light_pass(i)
+            rt_ref.taa_pass(True)
+            out = np.zeros((h, w, 4), np.float32)
+            rt_ref.read_owned(R.IMG_LIGHT, out)
+            rt_ref.swap_light_history()
+            seq_ref.append(out)
+        assert all(np.array_equal(seq_ref[i], ref_frames[i]) for i in range(len(gbs)))
+        rt.prefetch_gbuffer(*[t.numpy() for t in pinned[0]])
+        for i in range(n):
+            s2, gb = gbs[i % len(gbs)]
+            rt.set_scene(s2["scene"])
+            rt.flip_gbuffer()
+            if order == "early" and i + 1 < n:
+                rt.prefetch_gbuffer(*[t.numpy() for t in pinned[(i + 1) % len(gbs)]])
+            rt.light_pass(i)
+            rt.taa_pass(True)
+            rt.read_wait()
+            rt.read_owned_async(R.IMG_LIGHT, outs[i].numpy())
+            rt.swap_light_history()
+            if order == "late" and i + 1 < n:
+                rt.prefetch_gbuffer(*[t.numpy() for t in pinned[(i + 1) % len(gbs)]])
         rt.read_wait()
-        rt.read_owned_async(R.IMG_LIGHT, outs[i].numpy())
-        rt.swap_light_history()
-        if i + 1 < len(gbs):
-            rt.prefetch_gbuffer(*[t.numpy() for t in pinned[i + 1]])
-    rt.read_wait()
-    rt.sync()
-    for i in range(len(gbs)):
-        assert np.array_equal(outs[i].numpy(), ref_frames[i]), "frame %d differs" % i
+        rt.sync()
+        for i in range(n):
+            assert np.array_equal(outs[i].numpy(), seq_ref[i]), "%s: frame %d differs" % (order, i)
     with pytest.raises(R.LuzError):
         rt.flip_gbuffer()  # nothing prefetched
 
