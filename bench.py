@@ -204,7 +204,7 @@ def run_ours(args):
 
     # per-kernel times, measured live with CUDA events on the launch stream (a few extra frames)
     kt = {"light_ms": [], "taa_ms": [], "gather_ms": [], "tlas_ms": [], "gbuffer_ms": [], "volumetric_ms": [],
-          "shadow_map_ms": []}
+          "shadow_map_ms": [], "light_rays_ms": []}
     for i in range(min(args.steps, 8)):
         step(1 + args.warmup + args.steps + i)
         t = rt.read(R.TIMINGS)
@@ -349,6 +349,7 @@ def run_ours(args):
                               "NOT flushed: G-buffer + 3 light buffers = %.0f MB fit the 126 MB L2 (reference-size config, "
                               "reported for parity, not a roofline claim)") % (W * Hh * 80 / 1e6)},
             "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6]),
+                           "light_rays": kavg["light_rays_ms"], "light_shade": kavg["light_ms"] - kavg["light_rays_ms"],
                            "light_per_rank": [round(v, 4) for v in per_rank_light],
                            "volumetric": kavg["volumetric_ms"] if args.volumetric else 0.0,
                            "shadow_map": kavg["shadow_map_ms"] if (args.shadow_type == 2 or args.volumetric == 2) else 0.0},
@@ -358,18 +359,21 @@ def run_ours(args):
             # L1/L2 resident, so the same algorithmic bytes are also shown against the L2 read bandwidth probed in
             # this run (roofline_l2).  traffic = ncu dram bytes per launch of the committed profile, when it is for
             # this workload.
-            "roofline": {"kernel": "k_light_pass (fused shading + any-hit traversal)", "bound": "hbm",
+            "roofline": {"kernel": "light pass = k_light_rays (ray generation + any-hit traversal, the dominant kernel) + "
+                                   "k_light_shade (Cook-Torrance), timed together", "bound": "hbm",
                          "achieved": light_bytes / (light_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": light_bytes / (light_ms * 1e6) / hbm_peak, "traffic": ncu_traffic(args, "k_light_pass"),
+                         "frac": light_bytes / (light_ms * 1e6) / hbm_peak, "traffic": ncu_traffic(args, "light_pass"),
                          "peak_source": hbm_src,
-                         "algorithmic_bytes": "48 B/px streamed + 80 B/node + 48 B/triangle + 64 B/instance fetched per ray",
+                         "algorithmic_bytes": "SURVEY 8(d): 48 B/px streamed (32 B G-buffer + 16 B radiance) + per ray 80 B/node "
+                                              "+ 48 B/triangle + 64 B/instance (the 80 B is the contract's figure for a "
+                                              "compressed node; this build fetches 208-B fp32 nodes)",
                          "stream_bytes": 48.0 * W * shade_rows, "traversal_bytes": trav_bytes,
                          "bytes_per_ray": trav_bytes / max(rays_r, 1.0),
                          "nodes_per_ray": nodes / max(rays_r, 1.0),
                          "tris_per_ray": tris / max(rays_r, 1.0),
                          "instances_per_ray": insts / max(rays_r, 1.0),
                          "grays_per_s_per_gpu": rays_r / (light_ms * 1e6)},
-            "roofline_l2": {"kernel": "k_light_pass", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
+            "roofline_l2": {"kernel": "light pass (k_light_rays + k_light_shade)", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
                             "peak": l2_gbs, "unit": "GB/s", "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None,
                             "peak_source": "luzrt_probe_read_bandwidth, 32 MiB resident buffer, measured in this run"},
             "roofline_taa": {"kernel": "k_taa", "bound": "hbm", "achieved": 52.0 * own_px / (taa_ms * 1e6),

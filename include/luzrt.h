@@ -82,7 +82,8 @@ enum {
 
 /* luzrt_set_debug flags */
 enum {
-    LUZRT_DEBUG_MASKS = 1, /* light pass also writes the per-ray visibility bitmasks */
+    LUZRT_DEBUG_MASKS = 1, /* kept for ABI stability: the light pass always writes the per-ray visibility
+                              bitmasks (they carry the rays' results to its shading kernel)            */
     LUZRT_DEBUG_STATS = 2  /* light pass counts nodes / triangles / instances per ray */
 };
 
@@ -104,6 +105,7 @@ typedef struct luzrt_timings {
     float compose_ms; /* last luzrt_compose_pass   ("ComposePass", main.cpp:293)             */
     float volumetric_ms; /* last luzrt_volumetric_pass ("VolumetricLightPass", main.cpp:274)    */
     float shadow_map_ms; /* last luzrt_shadow_map_pass ("ShadowMaps", main.cpp:260)              */
+    float light_rays_ms; /* the ray kernel's share of light_ms (mask clears + k_light_rays)      */
 } luzrt_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

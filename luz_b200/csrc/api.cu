@@ -59,7 +59,7 @@ struct Texture {
     uint2 size{0, 0};
 };
 
-enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_VOLUMETRIC, EV_SHADOWMAP, EV_COUNT };
+enum { EV_TLAS, EV_GBUF, EV_LIGHT, EV_TAA, EV_GATHER, EV_COMPOSE, EV_VOLUMETRIC, EV_SHADOWMAP, EV_LIGHT_RAYS, EV_COUNT };
 
 } // namespace
 
@@ -994,12 +994,10 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     if (!c->blue_noise) return fail(c, LUZRT_E_STATE, "luzrt_set_blue_noise has not been called");
     DeviceGuard g(c->device);
     const bool stats = (c->debug & LUZRT_DEBUG_STATS) != 0;
-    // the shadow-map variant of the kernel is compiled with and without (masks + stats) only
-    const bool masks = (c->debug & LUZRT_DEBUG_MASKS) != 0 || (stats && c->fc.shadow_type == LUZW_SHADOW_MAP);
     if (c->fc.shadow_type == LUZW_SHADOW_MAP && !c->shadow_maps_current)
         return fail(c, LUZRT_E_STATE, "shadowType 2: luzrt_shadow_map_pass has not been called for this scene block");
     const size_t px = (size_t)c->w * c->h;
-    if (masks) {
+    { // the visibility masks carry the rays' results from the ray kernel to the shading kernel
         const size_t sw = std::max<size_t>((c->shadow_bits + 31) / 32, 1);
         const size_t aw = std::max<size_t>(((size_t)c->fc.ao_num_samples + 31) / 32, 1);
         int rc;
@@ -1037,8 +1035,10 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     ev_begin(c, EV_LIGHT);
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
-    CU(c, launch_light_pass(c->stream, a, masks, stats));
-    c->launches++;
+    CU(c, cudaEventRecord(c->ev[EV_LIGHT_RAYS][0], c->stream));
+    CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1]));
+    c->ev_valid[EV_LIGHT_RAYS] = true;
+    c->launches += 2;
     ev_end(c, EV_LIGHT);
     return LUZRT_OK;
 }
@@ -1295,7 +1295,7 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
         float ms[EV_COUNT] = {0};
         for (int i = 0; i < EV_COUNT; i++)
             if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], c->ev[i][0], c->ev[i][1]);
-        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC], ms[EV_SHADOWMAP]};
+        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC], ms[EV_SHADOWMAP], ms[EV_LIGHT_RAYS]};
         memcpy(dst, &t, sizeof(t));
         return LUZRT_OK;
     }

@@ -1,11 +1,20 @@
-// light_pass.cu -- the fused deferred lighting kernel: G-buffer decode, Cook-Torrance shading,
-// shadow-ray and AO-ray generation, any-hit traversal and accumulation in one launch, with all
-// per-ray state in registers (no ray buffers ever touch HBM).
+// light_pass.cu -- the deferred lighting pass as two kernels: k_light_rays fires every shadow and AO ray of
+// light.frag and leaves one bit per ray (1 = occluded) in the per-pixel visibility masks (all ray state in
+// registers, no ray buffers in HBM); k_light_shade evaluates light.frag:171-235 with the occluded fractions read
+// back from those bits.
 //
-// Restates source/Shaders/light.frag:171-235 (main), :86-109 (TraceShadowRay), :111-135
-// (TraceAORays), :137-169 (EvaluateShadow), :57-75 (samplers) and :17-49 (BRDF) of the reference;
-// launched where DeferredRenderer::LightPass (DeferredRenderer.cpp:324-345) draws its quad.
-// One warp shades an 8x4 pixel tile; the light list is staged in shared memory.
+// Why two kernels: a single fused kernel (this file up to commit "Host path: read-back in flight ...") keeps the whole
+// BRDF state of the pixel alive inside the traversal loop (albedo, F0, V, Lo, roughness ... ~30 registers) next to
+// ~45 registers of traversal state, which at the occupancy that hides the traversal's latencies best (80 registers,
+// 6 CTAs of 128 threads per SM) is spilled to local memory inside the hottest loop.  The ray kernel only carries what
+// ray generation needs (fragPos, N, blue noise); the shading kernel has no traversal in it and runs at full lane
+// utilisation.  The price is a second read of the G-buffer and 4 * (shadow_words + ao_words) bytes per pixel of
+// mask traffic, ~0.1 ms of HBM time at 4K.  Measured on B200 against the fused kernel (bit-identical results):
+// C3 7.31 -> 7.10 ms, C4 134.5 -> 125.5 ms, C2 1.00 -> 0.94 ms.
+//
+// Restates source/Shaders/light.frag:171-235 (main), :86-109 (TraceShadowRay), :111-135 (TraceAORays), :137-169
+// (EvaluateShadow), :57-75 (samplers), :17-49 (BRDF); launched where DeferredRenderer::LightPass
+// (DeferredRenderer.cpp:324-345) draws its quad.
 #include <cstdlib>
 
 #include "passes.h"
@@ -19,12 +28,11 @@ constexpr float kPI = 3.14159265359f;              // LuzCommon.h:11
 constexpr float kGoldenRatio = 2.118033988749895f; // LuzCommon.h:12 (sic)
 constexpr int kLightChunk = 256;
 constexpr int kMinCandSamples = 6; // below this the one TLAS walk per pixel does not pay for itself (C2: 4 spp)
-constexpr int kMaxCand = 8; // instances an AO candidate list can hold per pixel before falling back to the root descent
+constexpr int kMaxCand = 8;        // instances an AO candidate list holds before falling back to the root descent
 
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
 
-// light.frag:71-75.  The multiply and the add are rounded separately (no FMA) so that the sample
-// sequence is bit-identical to the oracle's plain fp32 evaluation.
+// light.frag:71-75, multiply and add rounded separately (bit-identical to the oracle's plain fp32)
 __device__ __forceinline__ float2 blue_noise_sample(float bn_r, float bn_g, int i, int frame_mod) {
     const float k = (float)(128 * i + frame_mod);
     const float off = __fmul_rn(kGoldenRatio, k);
@@ -48,14 +56,46 @@ __device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughne
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
-// SMAP: the variant launched when scene.shadowType == SHADOW_TYPE_MAP (light.frag:147-165); kept out of the
-// ray-traced variants so that their register allocation is untouched.
-template <bool MASKS, bool STATS, int MIN_BLOCKS, bool SMAP = false>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs a) {
+// number of set bits among bits [b0, b0 + n) of a pixel's mask words
+__device__ __forceinline__ uint32_t count_bits(const uint32_t* __restrict__ m, uint32_t b0, int n) {
+    uint32_t c = 0;
+    while (n > 0) {
+        const uint32_t w = __ldg(m + (b0 >> 5)), s = b0 & 31u;
+        const uint32_t take = min((uint32_t)n, 32u - s);
+        const uint32_t sel = take == 32u ? 0xFFFFFFFFu : ((1u << take) - 1u);
+        c += __popc((w >> s) & sel);
+        b0 += take;
+        n -= (int)take;
+    }
+    return c;
+}
+
+// Appends one visibility bit to a pixel's mask; words are stored when they fill up (and by flush()).
+struct BitWriter {
+    uint32_t* words;
+    uint32_t bit = 0, cur = 0;
+    __device__ __forceinline__ void push(bool set) {
+        if (set) cur |= 1u << (bit & 31u);
+        bit++;
+        if ((bit & 31u) == 0u) {
+            if (cur) words[(bit >> 5) - 1u] = cur; // the masks are cleared before the launch
+            cur = 0;
+        }
+    }
+    __device__ __forceinline__ void flush() {
+        if (cur) words[bit >> 5] = cur;
+        cur = 0;
+    }
+};
+
+// ---- kernel 1: rays ------------------------------------------------------------------------------------------
+// One warp = 8x4 pixel tile; lights staged in shared memory; one loop over "ray sources" (the lights, then one
+// pseudo source for AO) so that the kernel holds a single inlined copy of the traversal.
+template <bool STATS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
-    // per-thread AO candidate lists, [k][thread] so that a warp's accesses are conflict free
-    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw + a.cand_offset) + threadIdx.x;
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw + a.cand_offset) + threadIdx.x; // [k][thread]
 
     const FrameConst& fc = a.fc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -63,61 +103,31 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
     const uint32_t r = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool in_image = x < fc.width && r < a.rows.rows;
     const uint32_t y = in_image ? band_row(fc, a.rows, blockIdx.z, r) : 0u;
-    const size_t pix = (size_t)y * fc.width + x;                  // G-buffer, masks: natural row order
-    const size_t opix = (size_t)storage_row(fc, y) * fc.width + x; // light image: banded storage order
+    const size_t pix = (size_t)y * fc.width + x;
 
-    // ---- G-buffer fetch (light.frag:172-176; texel loads, SURVEY section 9 item 13) ----
     float3 N = f3(0.0f, 0.0f, 0.0f);
-    uchar4 a8 = make_uchar4(0, 0, 0, 0), m8 = a8, e8 = a8;
     float depth = 1.0f;
-    uchar4 bn8 = a8;
+    uchar4 bn8 = make_uchar4(0, 0, 0, 0);
     if (in_image) {
         const float4 n4 = __ldg(a.normal + pix);
         N = f3(n4.x, n4.y, n4.z);
-        a8 = __ldg(a.albedo + pix);
-        m8 = __ldg(a.material + pix);
-        e8 = __ldg(a.emission + pix);
         depth = __ldg(a.depth + pix);
-        // gl_FragCoord = (x+.5, y+.5); ivec2(mod(fragCoord, size)) == (x % w, y % h)
         bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
     }
-    const float3 ambientLight = f3(fc.ambient[0], fc.ambient[1], fc.ambient[2]);
-    const bool lit = in_image && (length3(N) != 0.0f); // :178
-    if (in_image && !lit) a.out[opix] = make_float4(ambientLight.x, ambientLight.y, ambientLight.z, 1.0f);
-
-    const float3 albedo = f3(powf((float)a8.x / 255.0f, 2.2f), powf((float)a8.y / 255.0f, 2.2f),
-                             powf((float)a8.z / 255.0f, 2.2f));
-    const float roughness = (float)m8.x / 255.0f, metallic = (float)m8.y / 255.0f, occlusion = (float)m8.z / 255.0f;
+    const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
     const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
     const float3 fragPos = depth_to_world(fc, u, v, depth);
     const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
-    const float3 V = normalize3(camPos - fragPos);
-    const float3 F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - metallic) + albedo * metallic;
     const float camDist = length3(fragPos - camPos);
     const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
-    const float NdotV = fmaxf(dot3(N, V), 0.0f);
-    const float ggxV = geometry_schlick_ggx(NdotV, roughness);
 
-    float3 Lo = f3(0.0f, 0.0f, 0.0f);
     uint2 stack[LUZ_STACK_SIZE];
     LocalStats st = {0, 0, 0};
     uint32_t n_rays = 0, n_occl = 0;
-    // halo rows of a partitioned frame are recomputation: their rays are not frame rays
-    const uint32_t counted = (r >= a.count_row_begin && r < a.count_row_end) ? 1u : 0u;
-    uint32_t* smask = nullptr;
-    uint32_t* amask = nullptr;
-    if (MASKS && in_image) {
-        smask = a.shadow_mask + pix * a.shadow_words;
-        amask = a.ao_mask + pix * a.ao_words;
-        for (uint32_t k = 0; k < a.shadow_words; k++) smask[k] = 0;
-        for (uint32_t k = 0; k < a.ao_words; k++) amask[k] = 0;
-    }
-    uint32_t shadow_bit = 0;
+    const uint32_t counted = (r >= a.count_row_begin && r < a.count_row_end) ? 1u : 0u; // halo rows are recomputation
+    BitWriter bits; // the shadow bits of all lights in light order, then (restarted) the AO bits
+    bits.words = a.shadow_mask + pix * a.shadow_words;
 
-    // One loop over "ray sources": the lights of the scene (shadow rays, light.frag:192-227) followed by
-    // one pseudo source for ambient occlusion (light.frag:229-231), so that the kernel contains a single
-    // inlined copy of the traversal (instruction-cache footprint) and every ray goes through one call site.
-    float rayTracedAo = 1.0f;
     const int n_sources = fc.num_lights + 1;
     for (int base = 0; base < n_sources; base += kLightChunk) {
         const int chunk = min(kLightChunk, n_sources - base);
@@ -129,16 +139,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
         if (!lit) continue;
         for (int li = 0; li < chunk; li++) {
             const bool is_ao = base + li == fc.num_lights;
-            // ---- per-source set-up ----
-            float3 O, L = f3(0.0f, 0.0f, 0.0f), T, B, C; // ray origin, light dir, sampling frame (T, B, C)
-            float attenuation = 1.0f, radius = 0.0f, tMinRay, tMaxRay;
-            float4 lcolor = f4(0.0f, 0.0f, 0.0f, 0.0f);
+            float3 O, T, B, C; // ray origin and sampling frame
+            float radius = 0.0f, tMinRay, tMaxRay;
             int n_samples;
             int n_cand = -1; // < 0: rays descend from the TLAS root
-            bool directional_or_shadowless = false;
-            float3 lposv = f3(0.0f, 0.0f, 0.0f);
-            int ltype = 0, lsmap = -1;
             if (is_ao) { // TraceAORays (light.frag:111-135)
+                bits.flush();
+                bits.words = a.ao_mask + pix * a.ao_words;
+                bits.bit = 0;
                 O = fragPos + N * (camDist * 0.01f);
                 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
                 B = cross3(N, T);
@@ -147,8 +155,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                 tMaxRay = fc.ao_max;
                 n_samples = fc.ao_num_samples;
                 if (n_samples >= kMinCandSamples) {
-                    // every AO ray of this pixel stays inside O +- aoMax * |dir| per axis, and
-                    // |dir_k| = |T_k h.x + B_k h.y + N_k h.z| <= sqrt(T_k^2 + B_k^2 + N_k^2) * |h| with |h| = 1 (+ rounding):
+                    // every AO ray of this pixel stays inside O +- aoMax * |dir| per axis (|dir_k| <= |(T_k, B_k, N_k)|):
                     // one TLAS walk with that box replaces the TLAS levels of all aoNumSamples rays
                     const float m = fabsf(tMaxRay) * 1.001f;
                     const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
@@ -158,46 +165,28 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                 }
             } else {
                 const LightRec L4 = s_lights[li];
+                n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
+                if (n_samples <= 0) continue; // no rays, no bits (light.frag:87-89)
                 const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
                 const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
                 const float3 Lvec = lpos - fragPos;
                 const float dist = length3(Lvec);
-                L = Lvec / dist; // normalize(L_)
-                if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
-                    L = normalize3(-ldir);
-                } else if (L4.type == LUZW_LIGHT_SPOT) {
-                    attenuation = 1.0f / (dist * dist);
-                    const float theta = dot3(L, normalize3(-ldir));
-                    const float epsilon = L4.position_inner.w - L4.direction_outer.w;
-                    attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
-                } else if (L4.type == LUZW_LIGHT_POINT) {
-                    attenuation = 1.0f / (dist * dist);
-                }
-                lcolor = L4.color_intensity;
+                float3 L = Lvec / dist;
+                if (L4.type == LUZW_LIGHT_DIRECTIONAL) L = normalize3(-ldir);
                 radius = L4.radius;
-                // EvaluateShadow (light.frag:137-169) + TraceShadowRay set-up (:86-98)
+                // EvaluateShadow (light.frag:137-146) + TraceShadowRay set-up (:86-98)
                 O = fragPos + N * fmaxf(camDist * 0.01f, 0.05f);
                 C = (L4.type == LUZW_LIGHT_DIRECTIONAL) ? ldir * dot3(ldir, L) * dist : L * dist;
                 T = normalize3(cross3(C, f3(0.0f, 1.0f, 0.0f)));
                 B = normalize3(cross3(T, C));
                 tMinRay = 0.001f;
                 tMaxRay = length3(C);
-                n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
-                directional_or_shadowless = fc.shadow_type != LUZW_SHADOW_RAYTRACING;
-                if (SMAP) {
-                    lposv = lpos;
-                    ltype = L4.type;
-                    lsmap = L4.shadow_map;
-                }
             }
-            // ---- the rays of this source ----
-            float hits = 0.0f;
-            int n_trace = n_samples;
             if (n_cand == 0) { // no instance within reach of any AO ray of this pixel: every one of them misses
                 n_rays += counted * (uint32_t)max(n_samples, 0);
-                n_trace = 0;
+                continue;
             }
-            for (int i = 0; i < n_trace; i++) {
+            for (int i = 0; i < n_samples; i++) {
                 const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
                 float sn, cs;
                 float3 dir;
@@ -211,58 +200,16 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
                     dir = normalize3(C + (pointRadius * cs) * T + (pointRadius * sn) * B);
                 }
                 n_rays += counted;
-                if (trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand)) {
-                    hits += 1.0f;
-                    n_occl += counted;
-                    if (MASKS) {
-                        if (is_ao) {
-                            amask[i >> 5] |= 1u << (i & 31);
-                        } else {
-                            const uint32_t b = shadow_bit + (uint32_t)i;
-                            smask[b >> 5] |= 1u << (b & 31u);
-                        }
-                    }
-                }
+                const bool hit = trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand);
+                n_occl += hit ? counted : 0u;
+                bits.push(hit);
             }
-            if (is_ao) {
-                if (n_samples != 0) rayTracedAo = ((float)n_samples - hits) / (float)n_samples; // ao / aoNumSamples
-                continue;
-            }
-            shadow_bit += (uint32_t)max(n_samples, 0);
-            // shadow factor: RT with samples -> occluded fraction; RT with 0 samples -> 0; otherwise 1 (:166-168)
-            float shadowFactor = directional_or_shadowless ? 1.0f : 0.0f;
-            if (n_samples > 0) shadowFactor = hits / (float)n_samples;
-            if (SMAP && fc.shadow_type == LUZW_SHADOW_MAP && lsmap != -1) // light.frag:147-165
-                shadowFactor = shadow_map_factor(a.shadow_maps[base + li], ltype, lposv, fragPos, O);
-            const float3 lcol = f3(lcolor.x, lcolor.y, lcolor.z);
-            const float3 radiance = lcol * lcolor.w * attenuation * (1.0f - shadowFactor);
-
-            const float3 H = normalize3(V + L);
-            const float NDF = distribution_ggx(N, H, roughness);
-            const float NdotL = fmaxf(dot3(N, L), 0.0f);
-            const float G = geometry_schlick_ggx(NdotL, roughness) * ggxV; // GeometrySmith :38-45
-            const float fp = powf(clampf(1.0f - clampf(dot3(H, V), 0.0f, 1.0f), 0.0f, 1.0f), 5.0f);
-            const float3 F = F0 + (f3(1.0f, 1.0f, 1.0f) - F0) * fp; // FresnelSchlick :47-49
-            const float3 num = NDF * G * F;
-            const float denom = 4.0f * NdotV * NdotL + 0.0001f;
-            const float3 spec = num / denom;
-            float3 kD = f3(1.0f, 1.0f, 1.0f) - F;
-            kD = kD * (1.0f - metallic);
-            Lo = Lo + (kD * albedo / kPI + spec) * radiance * NdotL;
         }
     }
-
-    if (lit) {
-        const float3 emission = f3((float)e8.x / 255.0f, (float)e8.y / 255.0f, (float)e8.z / 255.0f);
-        const float3 ambient = ambientLight * albedo * occlusion * rayTracedAo;
-        const float3 color = ambient + Lo + emission;
-        a.out[opix] = make_float4(color.x, color.y, color.z, 1.0f);
-    }
+    if (lit) bits.flush();
 
     // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
-    // (no CTA-wide barrier here: warps of a tile finish at very different times)
-    const unsigned int lit_warp =
-        __popc(__ballot_sync(0xFFFFFFFFu, lit && r >= a.count_row_begin && r < a.count_row_end));
+    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted));
     if (lane == 0 && lit_warp)
         atomicAdd(a.lit_counters + 16 * ((blockIdx.x * 4u + (blockIdx.y + blockIdx.z * 7u) * 29u + warp) & 63u),
                   (unsigned long long)lit_warp);
@@ -284,41 +231,150 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_pass(const LightArgs 
     }
 }
 
+// ---- kernel 2: shading -----------------------------------------------------------------------------------------
+// SMAP: compiled with the shadow-map branch of EvaluateShadow (light.frag:147-165).
+template <bool SMAP>
+__global__ void __launch_bounds__(128) k_light_shade(const LightArgs a) {
+    __shared__ LightRec s_lights[kLightChunk];
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t x = blockIdx.x * 32 + lane;
+    const uint32_t r = blockIdx.y * 4 + warp;
+    const bool in_image = x < fc.width && r < a.rows.rows;
+    const uint32_t y = in_image ? band_row(fc, a.rows, blockIdx.z, r) : 0u;
+    const size_t pix = (size_t)y * fc.width + x;                   // G-buffer, masks: natural row order
+    const size_t opix = (size_t)storage_row(fc, y) * fc.width + x; // light image: banded storage order
+
+    // ---- G-buffer fetch (light.frag:172-176; texel loads, SURVEY section 9 item 13) ----
+    float3 N = f3(0.0f, 0.0f, 0.0f);
+    uchar4 a8 = make_uchar4(0, 0, 0, 0), m8 = a8, e8 = a8;
+    float depth = 1.0f;
+    if (in_image) {
+        const float4 n4 = __ldg(a.normal + pix);
+        N = f3(n4.x, n4.y, n4.z);
+        a8 = __ldg(a.albedo + pix);
+        m8 = __ldg(a.material + pix);
+        e8 = __ldg(a.emission + pix);
+        depth = __ldg(a.depth + pix);
+    }
+    const float3 ambientLight = f3(fc.ambient[0], fc.ambient[1], fc.ambient[2]);
+    const bool lit = in_image && (length3(N) != 0.0f); // :178
+    if (in_image && !lit) a.out[opix] = make_float4(ambientLight.x, ambientLight.y, ambientLight.z, 1.0f);
+
+    const float3 albedo = f3(powf((float)a8.x / 255.0f, 2.2f), powf((float)a8.y / 255.0f, 2.2f),
+                             powf((float)a8.z / 255.0f, 2.2f));
+    const float roughness = (float)m8.x / 255.0f, metallic = (float)m8.y / 255.0f, occlusion = (float)m8.z / 255.0f;
+    const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+    const float3 fragPos = depth_to_world(fc, u, v, depth);
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const float3 V = normalize3(camPos - fragPos);
+    const float3 F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - metallic) + albedo * metallic;
+    const float camDist = length3(fragPos - camPos);
+    const float NdotV = fmaxf(dot3(N, V), 0.0f);
+    const float ggxV = geometry_schlick_ggx(NdotV, roughness);
+    const uint32_t* smask = a.shadow_mask + pix * a.shadow_words;
+    const uint32_t* amask = a.ao_mask + pix * a.ao_words;
+
+    float3 Lo = f3(0.0f, 0.0f, 0.0f);
+    uint32_t shadow_bit = 0;
+    for (int base = 0; base < fc.num_lights; base += kLightChunk) {
+        const int chunk = min(kLightChunk, fc.num_lights - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < chunk * 4; k += blockDim.x)
+            reinterpret_cast<float4*>(s_lights)[k] = __ldg(reinterpret_cast<const float4*>(a.lights + base) + k);
+        __syncthreads();
+        if (!lit) continue;
+        for (int li = 0; li < chunk; li++) {
+            const LightRec L4 = s_lights[li];
+            const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
+            const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
+            const float3 Lvec = lpos - fragPos;
+            const float dist = length3(Lvec);
+            float3 L = Lvec / dist; // normalize(L_)
+            float attenuation = 1.0f;
+            if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
+                L = normalize3(-ldir);
+            } else if (L4.type == LUZW_LIGHT_SPOT) {
+                attenuation = 1.0f / (dist * dist);
+                const float theta = dot3(L, normalize3(-ldir));
+                const float epsilon = L4.position_inner.w - L4.direction_outer.w;
+                attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
+            } else if (L4.type == LUZW_LIGHT_POINT) {
+                attenuation = 1.0f / (dist * dist);
+            }
+            // shadow factor: RT with samples -> occluded fraction; RT with 0 samples -> 0; otherwise 1 (:166-168)
+            const int n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
+            float shadowFactor = fc.shadow_type != LUZW_SHADOW_RAYTRACING ? 1.0f : 0.0f;
+            if (n_samples > 0) {
+                shadowFactor = (float)count_bits(smask, shadow_bit, n_samples) / (float)n_samples;
+                shadow_bit += (uint32_t)n_samples;
+            }
+            if (SMAP && fc.shadow_type == LUZW_SHADOW_MAP && L4.shadow_map != -1) { // light.frag:147-165
+                const float3 O = fragPos + N * fmaxf(camDist * 0.01f, 0.05f);
+                shadowFactor = shadow_map_factor(a.shadow_maps[base + li], L4.type, lpos, fragPos, O);
+            }
+            const float3 lcol = f3(L4.color_intensity.x, L4.color_intensity.y, L4.color_intensity.z);
+            const float3 radiance = lcol * L4.color_intensity.w * attenuation * (1.0f - shadowFactor);
+
+            const float3 H = normalize3(V + L);
+            const float NDF = distribution_ggx(N, H, roughness);
+            const float NdotL = fmaxf(dot3(N, L), 0.0f);
+            const float G = geometry_schlick_ggx(NdotL, roughness) * ggxV; // GeometrySmith :38-45
+            const float fp = powf(clampf(1.0f - clampf(dot3(H, V), 0.0f, 1.0f), 0.0f, 1.0f), 5.0f);
+            const float3 F = F0 + (f3(1.0f, 1.0f, 1.0f) - F0) * fp; // FresnelSchlick :47-49
+            const float3 num = NDF * G * F;
+            const float denom = 4.0f * NdotV * NdotL + 0.0001f;
+            const float3 spec = num / denom;
+            float3 kD = f3(1.0f, 1.0f, 1.0f) - F;
+            kD = kD * (1.0f - metallic);
+            Lo = Lo + (kD * albedo / kPI + spec) * radiance * NdotL;
+        }
+    }
+    if (lit) {
+        float rayTracedAo = 1.0f;
+        const int n_ao = fc.ao_num_samples;
+        if (n_ao != 0) rayTracedAo = ((float)n_ao - (float)count_bits(amask, 0u, n_ao)) / (float)n_ao; // ao / aoNumSamples
+        const float3 emission = f3((float)e8.x / 255.0f, (float)e8.y / 255.0f, (float)e8.z / 255.0f);
+        const float3 ambient = ambientLight * albedo * occlusion * rayTracedAo;
+        const float3 color = ambient + Lo + emission;
+        a.out[opix] = make_float4(color.x, color.y, color.z, 1.0f);
+    }
+}
+
 } // namespace
 
-cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool masks, bool stats) {
+// The mask buffers (shadow_words / ao_words words per pixel) are part of the pass, not a debug option.
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done) {
     if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
-    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands);
+    const size_t px = (size_t)args.fc.width * args.fc.height;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
-    // resident CTAs per SM the production variant is compiled for (register cap = 65536 / (128 * n));
-    // LUZRT_LIGHT_MINB selects among the compiled variants for tuning runs
-    static const int minb = [] {
-        const char* e = getenv("LUZRT_LIGHT_MINB");
-        return e ? atoi(e) : 6;
+    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands);
+    static const int minb = [] { // resident CTAs per SM the ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
+        const char* e2 = getenv("LUZRT_LIGHT_MINB");
+        return e2 ? atoi(e2) : 6;
     }();
-    if (args.fc.shadow_type == LUZW_SHADOW_MAP) {
-        if (masks || stats)
-            k_light_pass<true, true, 4, true><<<grid, 128, smem, stream>>>(a2);
-        else
-            k_light_pass<false, false, 4, true><<<grid, 128, smem, stream>>>(a2);
-    } else if (masks && stats)
-        k_light_pass<true, true, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (masks)
-        k_light_pass<true, false, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (stats)
-        k_light_pass<false, true, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 3)
-        k_light_pass<false, false, 3><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 5)
-        k_light_pass<false, false, 5><<<grid, 128, smem, stream>>>(a2);
+    if (stats)
+        k_light_rays<true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 4)
-        k_light_pass<false, false, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 8)
-        k_light_pass<false, false, 8><<<grid, 128, smem, stream>>>(a2);
-    else // 6 resident CTAs (80 registers, a few spilled values in L1) beat 4 (128 registers) by 5 % on C3/C4/C2
-        k_light_pass<false, false, 6><<<grid, 128, smem, stream>>>(a2);
+        k_light_rays<false, 4><<<grid, 128, smem, stream>>>(a2);
+    else if (minb == 5)
+        k_light_rays<false, 5><<<grid, 128, smem, stream>>>(a2);
+    else if (minb == 7)
+        k_light_rays<false, 7><<<grid, 128, smem, stream>>>(a2);
+    else // 6 resident CTAs (80 registers) beat 4, 5, 7 and 8 on C3 / C4 / C2 taken together (profiles/r1_ab_split.txt)
+        k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;
+    const dim3 sgrid((args.fc.width + 31) / 32, (args.rows.rows + 3) / 4, args.rows.n_bands);
+    if (args.fc.shadow_type == LUZW_SHADOW_MAP)
+        k_light_shade<true><<<sgrid, 128, 0, stream>>>(a2);
+    else
+        k_light_shade<false><<<sgrid, 128, 0, stream>>>(a2);
     return cudaGetLastError();
 }
 
