@@ -84,7 +84,8 @@ def build_luzrt(force=False, verbose=False):
 
 
 def NVCC_FLAGS_CMD(src, obj, extra=()):
-    return [NVCC] + NVCC_FLAGS + list(extra) + ["-c", src, "-o", obj]
+    # LUZ_EXTRA_NVCC: extra flags (e.g. -DLUZ_FAST_RAYGEN=0) for the A/B variants under build/variants
+    return [NVCC] + NVCC_FLAGS + list(extra) + os.environ.get("LUZ_EXTRA_NVCC", "").split() + ["-c", src, "-o", obj]
 
 
 def build_luzhost(force=False):

@@ -56,6 +56,46 @@ __device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughne
     return NdotV / (NdotV * (1.0f - k) + k);
 }
 
+// ---- ray generation arithmetic ---------------------------------------------------------------------------------
+// GLSL leaves the precision of normalize / sqrt / sin / cos to the driver (inversesqrt and sqrt 2 ulp, sin / cos 2^-11
+// absolute in the Vulkan precision table), and every desktop driver evaluates them on the special
+// function unit.  The ray kernel does the same: MUFU.RSQ / MUFU.SQRT / MUFU.SIN / MUFU.COS instead of the IEEE
+// division, square root and the 40-instruction sincosf, and explicit FMAs for the frame combination (ray generation was
+// 16 % of the kernel's issue slots).  Directions move by <= 1e-6 relative against the oracle's correctly rounded
+// evaluation, which only flips rays that graze an edge (the parity tests bound it: >= 99.9 % of the rays agree).  The
+// shading kernel keeps the correctly rounded forms: its output is compared value by value.
+#ifndef LUZ_FAST_RAYGEN
+#define LUZ_FAST_RAYGEN 1
+#endif
+#ifndef LUZ_AO_HEMISPHERE
+#define LUZ_AO_HEMISPHERE 1 // hemisphere reach boxes for the per-pixel AO candidate lists (traverse.cuh)
+#endif
+#if LUZ_FAST_RAYGEN
+__device__ __forceinline__ float rg_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float3 rg_normalize(float3 a) {
+    const float s = rsqrtf(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z))); // 0 -> inf -> NaN components, like a / 0
+    return f3(a.x * s, a.y * s, a.z * s);
+}
+__device__ __forceinline__ float rg_length(float3 a) { return rg_sqrt(fmaf(a.x, a.x, fmaf(a.y, a.y, a.z * a.z))); }
+__device__ __forceinline__ void rg_sincos(float x, float* sn, float* cs) { __sincosf(x, sn, cs); }
+// a * x + b * y + c * z
+__device__ __forceinline__ float3 rg_combine(float3 a, float x, float3 b, float y, float3 c, float z) {
+    return f3(fmaf(a.x, x, fmaf(b.x, y, c.x * z)), fmaf(a.y, x, fmaf(b.y, y, c.y * z)), fmaf(a.z, x, fmaf(b.z, y, c.z * z)));
+}
+#else
+__device__ __forceinline__ float rg_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float3 rg_normalize(float3 a) { return normalize3(a); }
+__device__ __forceinline__ float rg_length(float3 a) { return length3(a); }
+__device__ __forceinline__ void rg_sincos(float x, float* sn, float* cs) { sincosf(x, sn, cs); }
+__device__ __forceinline__ float3 rg_combine(float3 a, float x, float3 b, float y, float3 c, float z) {
+    return a * x + b * y + c * z;
+}
+#endif
+
 // number of set bits among bits [b0, b0 + n) of a pixel's mask words
 __device__ __forceinline__ uint32_t count_bits(const uint32_t* __restrict__ m, uint32_t b0, int n) {
     uint32_t c = 0;
@@ -158,10 +198,19 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
                     // every AO ray of this pixel stays inside O +- aoMax * |dir| per axis (|dir_k| <= |(T_k, B_k, N_k)|):
                     // one TLAS walk with that box replaces the TLAS levels of all aoNumSamples rays
                     const float m = fabsf(tMaxRay) * 1.001f;
-                    const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
-                                          m * sqrtf(T.y * T.y + B.y * B.y + C.y * C.y) + 1e-6f,
-                                          m * sqrtf(T.z * T.z + B.z * B.z + C.z * C.z) + 1e-6f);
-                    n_cand = collect_instances<STATS>(a.scene, O - ext, O + ext, s_cand, 128, kMaxCand, stack, &st);
+                    if (LUZ_AO_HEMISPHERE && tMinRay >= 0.0f && tMaxRay >= 0.0f) {
+                        // the rays only leave towards the hemisphere of C = N: hemisphere reach box (traverse.cuh),
+                        // then the same argument in the object space of every candidate against its BLAS root
+                        float3 lo, hi;
+                        hemisphere_box(O, T, B, C, m, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                        n_cand = collect_instances<STATS>(a.scene, lo, hi, s_cand, 128, kMaxCand, stack, &st);
+                        if (n_cand > 0) n_cand = filter_candidates<STATS>(a.scene, O, T, B, C, m, s_cand, 128, n_cand, &st);
+                    } else {
+                        const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
+                                              m * sqrtf(T.y * T.y + B.y * B.y + C.y * C.y) + 1e-6f,
+                                              m * sqrtf(T.z * T.z + B.z * B.z + C.z * C.z) + 1e-6f);
+                        n_cand = collect_instances<STATS>(a.scene, O - ext, O + ext, s_cand, 128, kMaxCand, stack, &st);
+                    }
                 }
             } else {
                 const LightRec L4 = s_lights[li];
@@ -170,17 +219,17 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
                 const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
                 const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
                 const float3 Lvec = lpos - fragPos;
-                const float dist = length3(Lvec);
-                float3 L = Lvec / dist;
-                if (L4.type == LUZW_LIGHT_DIRECTIONAL) L = normalize3(-ldir);
+                const float dist = rg_length(Lvec);
+                float3 L = rg_normalize(Lvec);
+                if (L4.type == LUZW_LIGHT_DIRECTIONAL) L = rg_normalize(-ldir);
                 radius = L4.radius;
                 // EvaluateShadow (light.frag:137-146) + TraceShadowRay set-up (:86-98)
                 O = fragPos + N * fmaxf(camDist * 0.01f, 0.05f);
                 C = (L4.type == LUZW_LIGHT_DIRECTIONAL) ? ldir * dot3(ldir, L) * dist : L * dist;
-                T = normalize3(cross3(C, f3(0.0f, 1.0f, 0.0f)));
-                B = normalize3(cross3(T, C));
+                T = rg_normalize(cross3(C, f3(0.0f, 1.0f, 0.0f)));
+                B = rg_normalize(cross3(T, C));
                 tMinRay = 0.001f;
-                tMaxRay = length3(C);
+                tMaxRay = rg_length(C);
             }
             if (n_cand == 0) { // no instance within reach of any AO ray of this pixel: every one of them misses
                 n_rays += counted * (uint32_t)max(n_samples, 0);
@@ -191,13 +240,13 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
                 float sn, cs;
                 float3 dir;
                 if (is_ao) { // HemisphereSample (light.frag:63-69)
-                    const float rr = sqrtf(rng.x);
-                    sincosf(6.283f * rng.y, &sn, &cs);
-                    dir = T * (rr * cs) + B * (rr * sn) + C * sqrtf(fmaxf(0.0f, 1.0f - rng.x));
+                    const float rr = rg_sqrt(rng.x);
+                    rg_sincos(6.283f * rng.y, &sn, &cs);
+                    dir = rg_combine(T, rr * cs, B, rr * sn, C, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
                 } else { // DiskSample (light.frag:57-61)
-                    const float pointRadius = radius * sqrtf(rng.x);
-                    sincosf(rng.y * 2.0f * kPI, &sn, &cs);
-                    dir = normalize3(C + (pointRadius * cs) * T + (pointRadius * sn) * B);
+                    const float pointRadius = radius * rg_sqrt(rng.x);
+                    rg_sincos(rng.y * 2.0f * kPI, &sn, &cs);
+                    dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
                 }
                 n_rays += counted;
                 const bool hit = trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand);

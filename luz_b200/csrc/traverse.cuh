@@ -251,6 +251,81 @@ __device__ __forceinline__ int collect_instances(const TraceScene& sc, const flo
     return n;
 }
 
+// ---- hemisphere reach ---------------------------------------------------------------------------------
+// The AO directions of a pixel are T h.x + B h.y + C h.z with h on the upper unit hemisphere (h.z >= 0,
+// light.frag:63-69) and 0 <= aoMin < t < aoMax, so along an axis whose frame coefficients are a = (T_k, B_k, C_k)
+// the segment end points stay inside O_k + reach * [dmin, dmax]:  dmax = |a| if a.z >= 0 (the maximiser a / |a| lies
+// on the hemisphere), else the rim value |a.xy|;  dmin likewise with the signs flipped.  For a pixel on a flat face
+// this box starts AT the (biased) origin instead of reaching one aoMax below the surface, which is what keeps the
+// pixel's own instance out of the candidate list.
+__device__ __forceinline__ void hemisphere_axis(const float ax, const float ay, const float az, float& dmin, float& dmax) {
+    const float r2 = fmaf(ax, ax, ay * ay);
+    const float len = sqrtf(fmaf(az, az, r2)), rim = sqrtf(r2);
+    dmax = az >= 0.0f ? len : rim;
+    dmin = az <= 0.0f ? -len : -rim;
+}
+__device__ __forceinline__ void hemisphere_box(const float3 O, const float3 T, const float3 B, const float3 C,
+                                               const float reach, const float3 slack, float3& lo, float3& hi) {
+    float mn, mx;
+    hemisphere_axis(T.x, B.x, C.x, mn, mx);
+    lo.x = fmaf(reach, mn, O.x) - slack.x, hi.x = fmaf(reach, mx, O.x) + slack.x;
+    hemisphere_axis(T.y, B.y, C.y, mn, mx);
+    lo.y = fmaf(reach, mn, O.y) - slack.y, hi.y = fmaf(reach, mx, O.y) + slack.y;
+    hemisphere_axis(T.z, B.z, C.z, mn, mx);
+    lo.z = fmaf(reach, mn, O.z) - slack.z, hi.z = fmaf(reach, mx, O.z) + slack.z;
+}
+
+// Drops from a candidate list (collect_instances) every instance whose BLAS the pixel's AO rays cannot reach: the
+// hemisphere frame goes to the instance's object space (the map is linear, so the hemisphere reach argument holds
+// there unchanged), and the reach box is tested against the exact fp32 boxes of the BLAS root's eight children.
+// Every triangle lies inside one of them, so a dropped instance holds no triangle any of the pixel's rays can hit:
+// visibility is unchanged, and each of the pixel's rays is spared the instance entry and the root visit (C3: 0.9
+// entries per AO ray before, almost all of them into the instance the pixel itself lies on).  The slack covers the
+// rounding of the transform (the rays are transformed one by one, with their own rounding, in trace_ray).
+// Returns the new count; NaN boxes (singular instance matrices) keep the candidate.
+template <bool STATS>
+__device__ __forceinline__ int filter_candidates(const TraceScene& sc, const float3 O, const float3 T, const float3 B,
+                                                 const float3 C, const float reach, uint32_t* cand, const int stride,
+                                                 const int n_cand, LocalStats* st) {
+    int kept = 0;
+    for (int k = 0; k < n_cand; k++) {
+        const uint32_t id = cand[k * stride];
+        const InstanceRec* rec = sc.instances + id;
+        const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1), r2 = __ldg(&rec->r2);
+        const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&rec->nodes));
+        const float3 Oo = xform_point(r0, r1, r2, O);
+        const float3 To = xform_dir(r0, r1, r2, T), Bo = xform_dir(r0, r1, r2, B), Co = xform_dir(r0, r1, r2, C);
+        // |terms| of the point transform: its rounding error is <= 4 * 2^-24 of their sum
+        const float3 mag = f3(fmaf(fabsf(r0.x), fabsf(O.x), fmaf(fabsf(r0.y), fabsf(O.y), fmaf(fabsf(r0.z), fabsf(O.z), fabsf(r0.w)))),
+                              fmaf(fabsf(r1.x), fabsf(O.x), fmaf(fabsf(r1.y), fabsf(O.y), fmaf(fabsf(r1.z), fabsf(O.z), fabsf(r1.w)))),
+                              fmaf(fabsf(r2.x), fabsf(O.x), fmaf(fabsf(r2.y), fabsf(O.y), fmaf(fabsf(r2.z), fabsf(O.z), fabsf(r2.w)))));
+        float3 lo, hi;
+        hemisphere_box(Oo, To, Bo, Co, reach, f3(2e-6f * mag.x + 1e-30f, 2e-6f * mag.y + 1e-30f, 2e-6f * mag.z + 1e-30f), lo, hi);
+        bool keep = !(lo.x <= hi.x && lo.y <= hi.y && lo.z <= hi.z); // NaN: leave it to trace_ray
+        if (!keep) {
+            const WideNode* root = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+            const float4* bp = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(root) + 16);
+            if (STATS) st->nodes++;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                const float4 lx = __ldg(bp + half), hx = __ldg(bp + 2 + half), ly = __ldg(bp + 4 + half);
+                const float4 hy = __ldg(bp + 6 + half), lz = __ldg(bp + 8 + half), hz = __ldg(bp + 10 + half);
+                const float alx[4] = {lx.x, lx.y, lx.z, lx.w}, ahx[4] = {hx.x, hx.y, hx.z, hx.w};
+                const float aly[4] = {ly.x, ly.y, ly.z, ly.w}, ahy[4] = {hy.x, hy.y, hy.z, hy.w};
+                const float alz[4] = {lz.x, lz.y, lz.z, lz.w}, ahz[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    keep |= alx[j] <= hi.x && ahx[j] >= lo.x && aly[j] <= hi.y && ahy[j] >= lo.y && alz[j] <= hi.z && ahz[j] >= lo.z;
+            }
+        }
+        if (keep) {
+            cand[kept * stride] = id;
+            kept++;
+        }
+    }
+    return kept;
+}
+
 // CLOSEST == false: any-hit, returns true at the first committed intersection.
 // CLOSEST == true : returns true if something was hit; *hit describes the nearest one.
 // n_cand < 0: descend from the TLAS root.  n_cand >= 0: visit only the instances cand[k * cand_stride]
@@ -285,11 +360,18 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     uint32_t pending = kNoInstance; // instance to enter at the top of the loop
     int ci = 0;
     float face_sign = 0.0f; // FACE_CULL: cull_sign * sign(det of the current instance's matrix)
-    rs = make_ray_space(o, d);
     inv_dd = 0.0f; // only triangles need it, and they live in object space
-    if (from_root) ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
-    // candidate mode keeps the world-space reciprocal direction for the box pre-test below
-    const float3 widir = rs.idir;
+    float3 widir; // candidate mode keeps the world-space reciprocal direction for the box pre-test below
+    if (from_root) {
+        rs = make_ray_space(o, d);
+        widir = rs.idir;
+        ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
+    } else { // no world-space node is ever tested: the ray space is set up per instance
+        widir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        rs.idir = widir;
+        rs.npn = rs.npf = f3(0.0f, 0.0f, 0.0f);
+        rs.off = 0u;
+    }
 
     while (true) {
         if (pending != kNoInstance) {

@@ -3,6 +3,10 @@
 usage: by_line.py report.ncu-rep [top_n]"""
 import collections, csv, io, subprocess, sys
 
+def num(v):
+    try: return int(v)
+    except ValueError: return 0
+
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
@@ -21,7 +25,7 @@ def main():
         try: n = int(r[ie])
         except ValueError: continue
         k = (cur_file, int(r[0]))
-        per[k] += n; smp[k] += int(r[ts] or 0); thr[k] += int(r[te] or 0); src[k] = r[1].strip()[:110]
+        per[k] += n; smp[k] += num(r[ts]); thr[k] += num(r[te]); src[k] = r[1].strip()[:110]
     tot = sum(per.values()) or 1; tots = sum(smp.values()) or 1
     byfile = collections.Counter()
     for (f, l), n in per.items(): byfile[f] += n

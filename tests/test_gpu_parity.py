@@ -275,6 +275,33 @@ def test_traversal_matches_exhaustive_random_mesh(rt_factory):
     compare_light(sc, 256, 144, 5, rt, exhaustive=True)
 
 
+def test_ao_candidate_lists_match_exhaustive(rt_factory):
+    """aoNumSamples >= 6 takes the per-pixel candidate-list path of the ray kernel (one TLAS box query per pixel with
+    the hemisphere reach box, candidates filtered against their BLAS root in object space, light_pass.cu /
+    traverse.cuh).  Non-convex triangle soup under rotated, anisotropically scaled instances packed closer than
+    aoMax, against the exhaustive oracle; also with a long aoMax (lists overflow -> root descent) and aoMin > 0."""
+    rng = np.random.default_rng(33)
+    nv, nt = 300, 200
+    verts = np.zeros((nv, 12), np.float32)
+    verts[:, :3] = rng.uniform(-1, 1, (nv, 3)).astype(np.float32)
+    verts[:, 3:6] = (0, 1, 0)
+    base = rng.integers(0, nv - 3, nt)
+    idx = np.stack([base, base + 1, base + 2], 1).astype(np.uint32).reshape(-1)
+    for ao_samples, ao_min, ao_max in ((8, 1e-4, 1.0), (16, 0.05, 0.6), (6, 1e-4, 6.0)):
+        rt = rt_factory()
+        sc = S.synthetic_scene(192, 108, grid=3, n_lights=1, light_samples=1, ao_samples=ao_samples, mixed_materials=False,
+                               eye=(5, 4, 6))
+        sc["scene"].ao_min, sc["scene"].ao_max = ao_min, ao_max
+        sc["meshes"].append((verts, idx))
+        for k in range(10):
+            m = S.trs((rng.uniform(-3, 3), rng.uniform(0.6, 1.6), rng.uniform(-3, 3)), rng.uniform(0, 360),
+                      (rng.uniform(0.4, 1.2), rng.uniform(0.2, 1.0), rng.uniform(0.4, 1.2)))
+            sc["instances"].append((1 if k % 2 else 0, m, 0))
+        r = compare_light(sc, 192, 108, 9, rt, exhaustive=True)
+        assert r["rays"] > 50000
+        rt.close()
+
+
 def test_tlas_refit_matches_rebuild(rt_factory):
     rt = rt_factory()
     w, h = 256, 144
