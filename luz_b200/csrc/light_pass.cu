@@ -415,7 +415,7 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         k_light_rays<false, 5><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 7)
         k_light_rays<false, 7><<<grid, 128, smem, stream>>>(a2);
-    else // 6 resident CTAs (80 registers) beat 4, 5, 7 and 8 on C3 / C4 / C2 taken together (profiles/r1_ab_split.txt)
+    else // 6 resident CTAs (80 registers) beat 4, 5, 7 and 8 on C3 / C4 / C2 taken together (profiles/r1_ab_split.md)
         k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;
