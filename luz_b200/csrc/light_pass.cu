@@ -67,9 +67,6 @@ __device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughne
 #ifndef LUZ_FAST_RAYGEN
 #define LUZ_FAST_RAYGEN 1
 #endif
-#ifndef LUZ_RAY_BATCH
-#define LUZ_RAY_BATCH 8 // rays a lane generates before it traces them back to back (trace_stream); 0: one at a time
-#endif
 #ifndef LUZ_AO_HEMISPHERE
 #define LUZ_AO_HEMISPHERE 1 // hemisphere reach boxes for the per-pixel AO candidate lists (traverse.cuh)
 #endif
@@ -171,21 +168,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
     BitWriter bits; // the shadow bits of all lights in light order, then (restarted) the AO bits
     bits.words = a.shadow_mask + pix * a.shadow_words;
 
-#if LUZ_RAY_BATCH > 0
-    float4* s_rays = reinterpret_cast<float4*>(smem_raw + a.ray_offset) + threadIdx.x; // [k][thread]: (dir, tmax)
-    int n_batch = 0, batch_cand = -1;
-    float3 batch_O = f3(0.0f, 0.0f, 0.0f);
-    float batch_tmin = 0.0f;
-    auto flush_batch = [&]() {
-        if (n_batch == 0) return;
-        trace_stream<STATS>(a.scene, batch_O, batch_tmin, s_rays, 128, n_batch, &st, stack, s_cand, 128, batch_cand,
-                            [&](bool hit) {
-                                n_occl += hit ? counted : 0u;
-                                bits.push(hit);
-                            });
-        n_batch = 0;
-    };
-#endif
     const int n_sources = fc.num_lights + 1;
     for (int base = 0; base < n_sources; base += kLightChunk) {
         const int chunk = min(kLightChunk, n_sources - base);
@@ -202,9 +184,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
             int n_samples;
             int n_cand = -1; // < 0: rays descend from the TLAS root
             if (is_ao) { // TraceAORays (light.frag:111-135)
-#if LUZ_RAY_BATCH > 0
-                flush_batch(); // the shadow rays still parked write their bits first
-#endif
                 bits.flush();
                 bits.words = a.ao_mask + pix * a.ao_words;
                 bits.bit = 0;
@@ -256,13 +235,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
                 n_rays += counted * (uint32_t)max(n_samples, 0);
                 continue;
             }
-#if LUZ_RAY_BATCH > 0
-            // rays are generated with the whole warp active into the lane's shared-memory batch and traced back to
-            // back by trace_stream; a batch holds rays of one origin / tmin / candidate list (shadow rays of
-            // successive lights share theirs, light.frag:138-139)
-            if (is_ao) flush_batch();
-            batch_O = O, batch_tmin = tMinRay, batch_cand = n_cand;
-#endif
             for (int i = 0; i < n_samples; i++) {
                 const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
                 float sn, cs;
@@ -277,20 +249,12 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
                     dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
                 }
                 n_rays += counted;
-#if LUZ_RAY_BATCH > 0
-                s_rays[n_batch * 128] = make_float4(dir.x, dir.y, dir.z, tMaxRay);
-                if (++n_batch == LUZ_RAY_BATCH) flush_batch();
-#else
                 const bool hit = trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand);
                 n_occl += hit ? counted : 0u;
                 bits.push(hit);
-#endif
             }
         }
     }
-#if LUZ_RAY_BATCH > 0
-    if (lit) flush_batch();
-#endif
     if (lit) bits.flush();
 
     // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
@@ -437,8 +401,7 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
-    a2.ray_offset = (a2.cand_offset + (uint32_t)sizeof(uint32_t) * kMaxCand * 128 + 15u) & ~15u;
-    const size_t smem = a2.ray_offset + sizeof(float4) * (size_t)(LUZ_RAY_BATCH > 0 ? LUZ_RAY_BATCH : 0) * 128;
+    const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
     const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands);
     static const int minb = [] { // resident CTAs per SM the ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
         const char* e2 = getenv("LUZRT_LIGHT_MINB");

@@ -506,186 +506,4 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     return found;
 }
 
-// ---- a lane's batch of any-hit rays, traversed back to back ---------------------------------------------
-// trace_ray joins the warp again after every ray, so each ray costs the warp as much as its slowest lane (an
-// occluded shadow ray ends at its first hit, an unoccluded one walks the whole segment).  trace_stream takes a
-// batch of rays per lane -- generated beforehand with all lanes active and parked in shared memory as
-// (dir.xyz, tmax), one origin and tmin for the batch -- and lets a lane that finishes a ray start its next one at
-// once: the warp then pays the slowest lane's SUM over the batch instead of the sum of the per-ray maxima.
-// Per ray the arithmetic is exactly trace_ray<false>'s (same ray set-up, node, triangle and candidate tests, same
-// order), so the visibility bits are identical; sink(hit) is called once per ray, in batch order.
-template <bool STATS, class Sink>
-__device__ __forceinline__ void trace_stream(const TraceScene& sc, const float3 wo, const float tmin, const float4* rays,
-                                             const int ray_stride, const int n_rays, LocalStats* st, uint2* stack,
-                                             const uint32_t* cand, const int cand_stride, const int n_cand, Sink&& sink) {
-    const bool from_root = n_cand < 0;
-    const bool origin_ok = wo.x == wo.x && wo.y == wo.y && wo.z == wo.z && tmin == tmin;
-    int next = 0;          // next ray of the batch
-    bool fetch = true;     // this lane needs a ray
-    bool have_result = false, result = false;
-
-    int sp = 0, inst_sp = -1, ci = 0;
-    float3 wd = f3(0.0f, 0.0f, 0.0f), o = wo, d = wd, widir = wd;
-    float tmax = 0.0f, inv_dd = 0.0f;
-    RaySpace rs;
-    rs.idir = rs.npn = rs.npf = wd;
-    rs.off = 0u;
-    const WideNode* nodes = sc.tlas_nodes;
-    const WideTri* tris = nullptr;
-    uint2 ngroup = make_uint2(0u, 0u), tgroup = make_uint2(0u, 0u);
-    uint32_t pending = kNoInstance;
-
-    while (true) {
-        if (fetch) {
-            bool got = false;
-            while (true) {
-                if (have_result) {
-                    sink(result);
-                    have_result = false;
-                }
-                if (next >= n_rays) break;
-                const float4 r = rays[next * ray_stride];
-                next++;
-                wd = f3(r.x, r.y, r.z);
-                tmax = r.w;
-                // rays with NaNs (e.g. the vertical-light tangent of light.frag:90) and null directions miss
-                const bool ok = origin_ok && wd.x == wd.x && wd.y == wd.y && wd.z == wd.z && tmax == tmax &&
-                                !(wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f);
-                if (!ok) {
-                    have_result = true;
-                    result = false;
-                    continue;
-                }
-                got = true;
-                break;
-            }
-            if (!got) break;
-            fetch = false;
-            sp = 0;
-            inst_sp = -1;
-            ci = 0;
-            pending = kNoInstance;
-            tgroup = make_uint2(0u, 0u);
-            o = wo;
-            d = wd;
-            nodes = sc.tlas_nodes;
-            if (from_root) {
-                rs = make_ray_space(o, d);
-                ngroup = make_uint2(0u, 0x80000000u);
-            } else {
-                widir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-                ngroup = make_uint2(0u, 0u);
-            }
-        }
-
-        if (pending != kNoInstance) {
-            const InstanceRec* rec = sc.instances + pending;
-            const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1), r2 = __ldg(&rec->r2);
-            const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&rec->nodes));
-            if (STATS) st->insts++;
-            o = xform_point(r0, r1, r2, wo);
-            d = xform_dir(r0, r1, r2, wd);
-            rs = make_ray_space(o, d);
-            inv_dd = fast_rcp(dot3_fma(d, d));
-            nodes = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
-            tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
-            pending = kNoInstance;
-            inst_sp = sp;
-            tgroup = make_uint2(0u, 0u);
-            const bool ok = (d.x == d.x && d.y == d.y && d.z == d.z && o.x == o.x && o.y == o.y && o.z == o.z) &&
-                            !(d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
-            ngroup = ok ? make_uint2(0u, 0x80000000u) : make_uint2(0u, 0u);
-        }
-
-        if (ngroup.y > 0x00FFFFFFu && tgroup.y == 0u) { // one node visit per pass
-            const uint32_t hits = ngroup.y;
-            const uint32_t imask = hits & 0xFFu;
-            const int bit = 31 - __clz(hits);
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
-            const int slot = bit - 24;
-            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
-            const WideNode* node = nodes + (ngroup.x + rel);
-            const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(node));
-            if (STATS) st->nodes++;
-            const uint32_t slots = intersect_node(node, rs, tmin, tmax);
-            const uint32_t node_imask = hdr.x >> 24;
-            ngroup = make_uint2(hdr.x & 0x00FFFFFFu, ((slots & node_imask) << 24) | node_imask);
-            tgroup = make_uint2(hdr.y, leaf_bits(slots & ~node_imask, hdr.z, hdr.w));
-        }
-
-        bool hit_now = false;
-        while (tgroup.y != 0u) {
-            const int j = __ffs(tgroup.y) - 1;
-            tgroup.y &= tgroup.y - 1u;
-            const uint32_t prim = tgroup.x + (uint32_t)j;
-            if (inst_sp < 0) { // TLAS leaf: postpone the rest of this node and enter the instance
-                if (tgroup.y != 0u) stack[sp++] = tgroup;
-                if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
-                pending = prim;
-                tgroup = make_uint2(0u, 0u);
-                ngroup = make_uint2(0u, 0u);
-                break;
-            }
-            const float4* tp = reinterpret_cast<const float4*>(tris + prim);
-            const float4 p0 = __ldg(tp + 0), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-            if (STATS) st->tris++;
-            float t, bu, bv;
-            if (tri_test(p0, p1, p2, o, d, inv_dd, tmin, tmax, t, bu, bv)) {
-                hit_now = true;
-                break;
-            }
-        }
-        if (hit_now) {
-            have_result = true;
-            result = true;
-            fetch = true;
-            continue;
-        }
-        if (pending != kNoInstance) continue;
-
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (inst_sp >= 0 && sp == inst_sp) { // BLAS exhausted
-                inst_sp = -1;
-                if (from_root) { // back to world space
-                    o = wo;
-                    d = wd;
-                    rs = make_ray_space(o, d);
-                    nodes = sc.tlas_nodes;
-                }
-            }
-            if (sp == 0) {
-                if (!from_root) { // next candidate whose world box the segment meets (see trace_ray)
-                    while (ci < n_cand) {
-                        const uint32_t id = cand[ci * cand_stride];
-                        ci++;
-                        const float4 blo = __ldg(sc.inst_boxes + 2 * id), bhi = __ldg(sc.inst_boxes + 2 * id + 1);
-                        const float tx0 = (blo.x - wo.x) * widir.x, tx1 = (bhi.x - wo.x) * widir.x;
-                        const float ty0 = (blo.y - wo.y) * widir.y, ty1 = (bhi.y - wo.y) * widir.y;
-                        const float tz0 = (blo.z - wo.z) * widir.z, tz1 = (bhi.z - wo.z) * widir.z;
-                        const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-                        const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-                        if (tn - tf <= 2e-6f * fmaxf(fabsf(tn), fabsf(tf))) {
-                            pending = id;
-                            break;
-                        }
-                    }
-                    if (pending != kNoInstance) continue;
-                }
-                have_result = true; // the ray is unoccluded
-                result = false;
-                fetch = true;
-                continue;
-            }
-            const uint2 e = stack[--sp];
-            if (e.y > 0x00FFFFFFu) {
-                ngroup = e;
-            } else { // a postponed primitive group
-                tgroup = e;
-                ngroup = make_uint2(0u, 0u);
-            }
-        }
-    }
-}
-
 } // namespace luz
