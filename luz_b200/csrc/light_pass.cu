@@ -131,8 +131,9 @@ struct BitWriter {
 // ---- kernel 1: rays ------------------------------------------------------------------------------------------
 // One warp = 8x4 pixel tile; lights staged in shared memory; one loop over "ray sources" (the lights, then one
 // pseudo source for AO) so that the kernel holds a single inlined copy of the traversal.
-template <bool STATS, int MIN_BLOCKS>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs a) {
+// PART -1: every ray of the pixel; 0: its shadow rays only; 1: its AO rays only (they write different mask arrays).
+template <bool STATS, int PART>
+__device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32_t band) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw + a.cand_offset) + threadIdx.x; // [k][thread]
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
     const uint32_t x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
     const uint32_t r = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
     const bool in_image = x < fc.width && r < a.rows.rows;
-    const uint32_t y = in_image ? band_row(fc, a.rows, blockIdx.z, r) : 0u;
+    const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
     const size_t pix = (size_t)y * fc.width + x;
 
     float3 N = f3(0.0f, 0.0f, 0.0f);
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
         if (!lit) continue;
         for (int li = 0; li < chunk; li++) {
             const bool is_ao = base + li == fc.num_lights;
+            if (PART == (is_ao ? 0 : 1)) continue; // the other CTA's rays
             float3 O, T, B, C; // ray origin and sampling frame
             float radius = 0.0f, tMinRay, tMaxRay;
             int n_samples;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
     if (lit) bits.flush();
 
     // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
-    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted));
+    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted && PART <= 0));
     if (lane == 0 && lit_warp)
         atomicAdd(a.lit_counters + 16 * ((blockIdx.x * 4u + (blockIdx.y + blockIdx.z * 7u) * 29u + warp) & 63u),
                   (unsigned long long)lit_warp);
@@ -278,6 +280,23 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs 
             atomicAdd(&a.stats->occluded, vals[4]);
         }
     }
+}
+
+template <bool STATS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs a) {
+    light_rays_body<STATS, -1>(a, blockIdx.z);
+}
+
+// The same work as two CTAs per tile: blockIdx.z = part * n_bands + band, part 0 fires the shadow rays, part 1 the AO
+// rays.  Halving the work of a CTA halves the tail of the launch, which is what a rank of a multi-GPU frame (1/8 of
+// the pixels, ~10 waves of CTAs whose cost varies from nothing for sky to ~300 us) loses most of its time to; on a
+// whole 4K frame the tail does not matter and the plain kernel is ~3 % faster (profiles/r1_ab_ray_parts.md).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_split(const LightArgs a) {
+    if (blockIdx.z < a.rows.n_bands)
+        light_rays_body<false, 0>(a, blockIdx.z);
+    else
+        light_rays_body<false, 1>(a, blockIdx.z - a.rows.n_bands);
 }
 
 // ---- kernel 2: shading -----------------------------------------------------------------------------------------
@@ -402,12 +421,23 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
-    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands);
+    // shadow and AO rays in separate CTAs when both exist and the launch is small enough for its tail to matter
+    // (LUZRT_RAY_PARTS=1 / 2 forces one / two CTAs per tile)
+    static const int parts_env = [] {
+        const char* e2 = getenv("LUZRT_RAY_PARTS");
+        return e2 ? atoi(e2) : 0;
+    }();
+    const bool any_shadow = args.fc.shadow_type == LUZW_SHADOW_RAYTRACING && args.fc.num_lights > 0;
+    const bool small = (size_t)args.rows.rows * args.rows.n_bands * 2 <= (size_t)args.fc.height; // a rank of >= 2
+    const bool split = !stats && any_shadow && args.fc.ao_num_samples > 0 && (parts_env == 2 || (parts_env == 0 && small));
+    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands * (split ? 2u : 1u));
     static const int minb = [] { // resident CTAs per SM the ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
         const char* e2 = getenv("LUZRT_LIGHT_MINB");
         return e2 ? atoi(e2) : 6;
     }();
-    if (stats)
+    if (split)
+        k_light_rays_split<6><<<grid, 128, smem, stream>>>(a2);
+    else if (stats)
         k_light_rays<true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 4)
         k_light_rays<false, 4><<<grid, 128, smem, stream>>>(a2);
