@@ -402,6 +402,11 @@ def test_banded_partition_matches_single_gpu(rt_factory):
             part = np.zeros((7, w, 4), np.float32)
             rt.read_rows(R.IMG_LIGHT, int(own[3]), int(own[3]) + 7, part)
             assert np.array_equal(part, full_res[int(own[3]):int(own[3]) + 7])
+            # without the statistics variant a rank's ray launch is k_light_rays_split (shadow and AO rays of a tile
+            # in separate CTAs, light_pass.cu): same bits
+            rt.set_debug(0)
+            rt.light_pass(3)
+            assert np.array_equal(rt.read(R.IMG_LIGHT)[shaded], full_light[shaded])
         assert rays == full_st.rays  # halo rows are recomputation, not frame rays
 
 
