@@ -682,10 +682,24 @@ __global__ void k_gather_triangles(const uint8_t* __restrict__ verts, uint32_t s
     const float* p0 = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t + 0] * stride);
     const float* p1 = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t + 1] * stride);
     const float* p2 = reinterpret_cast<const float*>(verts + (size_t)idx[3 * t + 2] * stride);
+    // explicitly rounded (no contraction): cross(q, p) must be the exact negation of cross(p, q)
+    const float3 a = f3(p0[0], p0[1], p0[2]), b = f3(p1[0], p1[1], p1[2]), c = f3(p2[0], p2[1], p2[2]);
+    auto crs = [](const float3 q, const float3 p) {
+        return f3(__fsub_rn(__fmul_rn(q.y, p.z), __fmul_rn(q.z, p.y)), __fsub_rn(__fmul_rn(q.z, p.x), __fmul_rn(q.x, p.z)),
+                  __fsub_rn(__fmul_rn(q.x, p.y), __fmul_rn(q.y, p.x)));
+    };
+    auto sub = [](const float3 q, const float3 p) { return f3(__fsub_rn(q.x, p.x), __fsub_rn(q.y, p.y), __fsub_rn(q.z, p.z)); };
+    const float3 mu = crs(c, b), mv = crs(a, c), mw = crs(b, a);
+    const float3 eu = sub(b, c), ev = sub(c, a), ew = sub(a, b);
+    const float3 n = crs(sub(b, a), sub(c, a));
+    const float kk = __fadd_rn(__fadd_rn(__fmul_rn(n.x, a.x), __fmul_rn(n.y, a.y)), __fmul_rn(n.z, a.z));
     WideTri w;
-    w.v0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(t));
-    w.v1 = make_float4(p1[0], p1[1], p1[2], 0.0f);
-    w.v2 = make_float4(p2[0], p2[1], p2[2], 0.0f);
+    w.mu = make_float4(mu.x, mu.y, mu.z, __uint_as_float(t));
+    w.eu = make_float4(eu.x, eu.y, eu.z, kk);
+    w.mv = make_float4(mv.x, mv.y, mv.z, n.x);
+    w.ev = make_float4(ev.x, ev.y, ev.z, n.y);
+    w.mw = make_float4(mw.x, mw.y, mw.z, n.z);
+    w.ew = make_float4(ew.x, ew.y, ew.z, 0.0f);
     tris[k] = w;
 }
 

@@ -28,11 +28,19 @@ struct __align__(16) WideNode {
 static_assert(sizeof(WideNode) == 208, "WideNode must be 208 bytes");
 constexpr uint32_t kMaxWideNodes = 1u << 24; // child_base is 24 bits
 
-// One triangle, 48 bytes: three float4 (xyz = vertex, v0.w = original triangle index bits).
+// One triangle, 96 bytes, prepared for the edge test in Pluecker coordinates (traverse.cuh tri_test): per edge the
+// moment q x p and the direction p - q of its two vertices, so that the signed volume of the ray against the edge is
+// six multiply-adds on the ray's (d, o x d) with no per-triangle translation; the plane (N, k = N . p0) gives t.
+// Reversing an edge negates its moment and its direction bit by bit, which is what makes shared edges watertight.
 struct __align__(16) WideTri {
-    float4 v0, v1, v2;
+    float4 mu; // xyz = p2 x p1 (edge opposite p0),  w = original triangle index bits
+    float4 eu; // xyz = p1 - p2,                     w = k = N . p0
+    float4 mv; // xyz = p0 x p2 (edge opposite p1),  w = N.x     N = (p1 - p0) x (p2 - p0)
+    float4 ev; // xyz = p2 - p0,                     w = N.y
+    float4 mw; // xyz = p1 x p0 (edge opposite p2),  w = N.z
+    float4 ew; // xyz = p0 - p1,                     w = 0
 };
-static_assert(sizeof(WideTri) == 48, "WideTri must be 48 bytes");
+static_assert(sizeof(WideTri) == 96, "WideTri must be 96 bytes");
 
 // One TLAS leaf record, 64 bytes: world->object 3x4 (rows) + the BLAS it points to.
 struct __align__(16) InstanceRec {

@@ -49,32 +49,42 @@ __device__ __forceinline__ float3 xform_dir(const float4 r0, const float4 r1, co
               fmaf(r2.x, v.x, fmaf(r2.y, v.y, r2.z * v.z)));
 }
 __device__ __forceinline__ float dot3_fma(const float3 a, const float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+__device__ __forceinline__ float3 cross3_rn(const float3 a, const float3 b) { // explicitly rounded, never contracted
+    return f3(__fsub_rn(__fmul_rn(a.y, b.z), __fmul_rn(a.z, b.y)), __fsub_rn(__fmul_rn(a.z, b.x), __fmul_rn(a.x, b.z)),
+              __fsub_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
 
-// Watertight two-sided ray/triangle test by signed volumes (scalar triple products) evaluated
-// with explicitly rounded operations: the edge function of a shared edge is bitwise
-// antisymmetric between the two triangles that share it, so no ray slips between them.
-__device__ __forceinline__ bool tri_test(const float4 p0, const float4 p1, const float4 p2, const float3 o,
-                                         const float3 d, const float inv_dd, const float tmin, const float tmax,
-                                         float& t_out, float& bu, float& bv) {
-    const float3 A = f3(p0.x - o.x, p0.y - o.y, p0.z - o.z);
-    const float3 B = f3(p1.x - o.x, p1.y - o.y, p1.z - o.z);
-    const float3 C = f3(p2.x - o.x, p2.y - o.y, p2.z - o.z);
-#define LUZ_TRIPLE(P, Q)                                                                                      \
-    __fadd_rn(__fadd_rn(__fmul_rn(d.x, __fsub_rn(__fmul_rn(P.y, Q.z), __fmul_rn(P.z, Q.y))),                  \
-                        __fmul_rn(d.y, __fsub_rn(__fmul_rn(P.z, Q.x), __fmul_rn(P.x, Q.z)))),                 \
-              __fmul_rn(d.z, __fsub_rn(__fmul_rn(P.x, Q.y), __fmul_rn(P.y, Q.x))))
-    const float U = LUZ_TRIPLE(C, B);
-    const float V = LUZ_TRIPLE(A, C);
-    const float W = LUZ_TRIPLE(B, A);
-#undef LUZ_TRIPLE
+// Watertight two-sided ray/triangle test by signed volumes in Pluecker coordinates.  With A = p0 - o etc. the volume
+// d . (C x B) of the ray against the edge (p1, p2) expands to d . (p2 x p1) + (p1 - p2) . (o x d): the builder stores
+// the edge's moment and direction (WideTri), the ray carries d and its moment m = o x d, and the
+// volume is six multiply-adds.  Reversing the edge negates moment and direction bit by bit and every multiply-add
+// below is odd in them, so the two triangles sharing an edge see exactly opposite values: no ray slips between them.
+// (The previous form translated the vertices by -o and cost 51 instructions up to the sign test; this one 18.)
+struct TriData {
+    float4 mu, eu, mv, ev, mw, ew;
+};
+__device__ __forceinline__ TriData load_tri(const WideTri* tri) {
+    const float4* tp = reinterpret_cast<const float4*>(tri);
+    TriData q;
+    q.mu = __ldg(tp + 0), q.eu = __ldg(tp + 1), q.mv = __ldg(tp + 2);
+    q.ev = __ldg(tp + 3), q.mw = __ldg(tp + 4), q.ew = __ldg(tp + 5);
+    return q;
+}
+__device__ __forceinline__ float edge_volume(const float3 d, const float3 m, const float4 M, const float4 E) {
+    return fmaf(d.x, M.x, fmaf(d.y, M.y, fmaf(d.z, M.z, fmaf(m.x, E.x, fmaf(m.y, E.y, __fmul_rn(m.z, E.z))))));
+}
+__device__ __forceinline__ bool tri_test(const TriData& q, const float3 o, const float3 d, const float3 m, const float tmin,
+                                         const float tmax, float& t_out, float& bu, float& bv) {
+    const float U = edge_volume(d, m, q.mu, q.eu);
+    const float V = edge_volume(d, m, q.mv, q.ev);
+    const float W = edge_volume(d, m, q.mw, q.ew);
     const float mn = fminf(U, fminf(V, W)), mx = fmaxf(U, fmaxf(V, W));
     if (mn < 0.0f && mx > 0.0f) return false;
     const float det = U + V + W;
     if (det == 0.0f) return false;
-    // hit point relative to the origin = (U*A + V*B + W*C) / det; t = (P . d) / (d . d)
-    const float3 P = f3(fmaf(U, A.x, fmaf(V, B.x, W * C.x)), fmaf(U, A.y, fmaf(V, B.y, W * C.y)),
-                        fmaf(U, A.z, fmaf(V, B.z, W * C.z)));
-    const float t = (fmaf(P.x, d.x, fmaf(P.y, d.y, P.z * d.z)) * inv_dd) / det;
+    // the plane: t = N . (p0 - o) / (N . d)
+    const float3 N = f3(q.mv.w, q.ev.w, q.mw.w);
+    const float t = (q.eu.w - dot3_fma(N, o)) / dot3_fma(N, d);
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
     bu = U / det;
@@ -350,7 +360,6 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
 
     float3 o = wo, d = wd;
     RaySpace rs;
-    float inv_dd;
     const WideNode* nodes = sc.tlas_nodes;
     const WideTri* tris = nullptr;
     bool found = false;
@@ -360,7 +369,6 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     uint32_t pending = kNoInstance; // instance to enter at the top of the loop
     int ci = 0;
     float face_sign = 0.0f; // FACE_CULL: cull_sign * sign(det of the current instance's matrix)
-    inv_dd = 0.0f; // only triangles need it, and they live in object space
     float3 widir; // candidate mode keeps the world-space reciprocal direction for the box pre-test below
     if (from_root) {
         rs = make_ray_space(o, d);
@@ -383,7 +391,6 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             o = xform_point(r0, r1, r2, wo);
             d = xform_dir(r0, r1, r2, wd);
             rs = make_ray_space(o, d);
-            inv_dd = fast_rcp(dot3_fma(d, d));
             if (FACE_CULL) {
                 // det of the world->object rows has the sign of det of the instance matrix
                 const float det = r0.x * (r1.y * r2.z - r1.z * r2.y) - r0.y * (r1.x * r2.z - r1.z * r2.x) +
@@ -437,14 +444,13 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 ngroup = make_uint2(0u, 0u);
                 break;
             } else {
-                const float4* tp = reinterpret_cast<const float4*>(tris + prim);
-                const float4 p0 = __ldg(tp + 0), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+                const TriData q = load_tri(tris + prim);
                 if (STATS) st->tris++;
                 float t, bu, bv;
-                if (tri_test(p0, p1, p2, o, d, inv_dd, tmin, tmax, t, bu, bv)) {
+                // the ray's moment is recomputed here rather than kept alive across the node loop (registers)
+                if (tri_test(q, o, d, cross3_rn(o, d), tmin, tmax, t, bu, bv)) {
                     if (FACE_CULL) { // front faces (in the framebuffer of the emulated view) are not rasterised
-                        const float3 e1 = f3(p1.x - p0.x, p1.y - p0.y, p1.z - p0.z), e2 = f3(p2.x - p0.x, p2.y - p0.y, p2.z - p0.z);
-                        const float3 n = cross3(e1, e2);
+                        const float3 n = f3(q.mv.w, q.ev.w, q.mw.w); // (p1 - p0) x (p2 - p0)
                         if (!(face_sign * dot3(d, n) > 0.0f)) continue;
                     }
                     if (!CLOSEST) return true;
@@ -452,7 +458,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                     found = true;
                     hit->t = t;
                     hit->inst = cur_inst;
-                    hit->prim = __float_as_uint(p0.w);
+                    hit->prim = __float_as_uint(q.mu.w);
                     hit->bu = bu;
                     hit->bv = bv;
                 }
