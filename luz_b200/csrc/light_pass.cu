@@ -27,7 +27,10 @@ namespace {
 constexpr float kPI = 3.14159265359f;              // LuzCommon.h:11
 constexpr float kGoldenRatio = 2.118033988749895f; // LuzCommon.h:12 (sic)
 constexpr int kLightChunk = 256;
-constexpr int kMinCandSamples = 6; // below this the one TLAS walk per pixel does not pay for itself (C2: 4 spp)
+#ifndef LUZ_MIN_CAND_SAMPLES
+#define LUZ_MIN_CAND_SAMPLES 6
+#endif
+constexpr int kMinCandSamples = LUZ_MIN_CAND_SAMPLES; // below this the one TLAS walk per pixel does not pay for itself
 constexpr int kMaxCand = 8;        // instances an AO candidate list holds before falling back to the root descent
 
 __device__ __forceinline__ float fractf(float x) { return x - floorf(x); }
@@ -132,7 +135,7 @@ struct BitWriter {
 // One warp = 8x4 pixel tile; lights staged in shared memory; one loop over "ray sources" (the lights, then one
 // pseudo source for AO) so that the kernel holds a single inlined copy of the traversal.
 // PART -1: every ray of the pixel; 0: its shadow rays only; 1: its AO rays only (they write different mask arrays).
-template <bool STATS, int PART>
+template <bool STATS, int PART, bool ONE_VISIT>
 __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32_t band) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
@@ -251,7 +254,7 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
                     dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
                 }
                 n_rays += counted;
-                const bool hit = trace_ray<false, STATS>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand);
+                const bool hit = trace_ray<false, STATS, false, ONE_VISIT>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand);
                 n_occl += hit ? counted : 0u;
                 bits.push(hit);
             }
@@ -284,19 +287,26 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
 
 template <bool STATS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs a) {
-    light_rays_body<STATS, -1>(a, blockIdx.z);
+    light_rays_body<STATS, -1, false>(a, blockIdx.z);
 }
 
-// The same work as two CTAs per tile: blockIdx.z = part * n_bands + band, part 0 fires the shadow rays, part 1 the AO
-// rays.  Halving the work of a CTA halves the tail of the launch, which is what a rank of a multi-GPU frame (1/8 of
-// the pixels, ~10 waves of CTAs whose cost varies from nothing for sky to ~300 us) loses most of its time to; on a
-// whole 4K frame the tail does not matter and the plain kernel is ~3 % faster (profiles/r1_ab_ray_parts.md).
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_split(const LightArgs a) {
+// Frames with one kind of ray only (PART 0: shadow rays, e.g. C4; PART 1: AO rays, e.g. shadowType == ShadowMap).
+template <int PART, bool ONE_VISIT>
+__global__ void __launch_bounds__(128, 6) k_light_rays_part(const LightArgs a) {
+    light_rays_body<false, PART, ONE_VISIT>(a, blockIdx.z);
+}
+
+// Both kinds: two CTAs per tile, blockIdx.z = part * n_bands + band, part 0 fires the shadow rays, part 1 the AO rays
+// (they write different mask arrays).  The bodies are specialised at compile time (the shadow body holds no candidate
+// list code, the AO body no light loop), which is worth 2-3 % on a whole 4K frame, and halving the work of a CTA
+// halves the tail of the launch, which is what a rank of a multi-GPU frame (1/8 of the pixels, ~10 waves of CTAs whose
+// cost varies from nothing for sky to ~300 us) loses most of its time to (profiles/r1_ab_ray_parts.md).
+template <bool ONE_VISIT>
+__global__ void __launch_bounds__(128, 6) k_light_rays_split(const LightArgs a) {
     if (blockIdx.z < a.rows.n_bands)
-        light_rays_body<false, 0>(a, blockIdx.z);
+        light_rays_body<false, 0, ONE_VISIT>(a, blockIdx.z);
     else
-        light_rays_body<false, 1>(a, blockIdx.z - a.rows.n_bands);
+        light_rays_body<false, 1, ONE_VISIT>(a, blockIdx.z - a.rows.n_bands);
 }
 
 // ---- kernel 2: shading -----------------------------------------------------------------------------------------
@@ -421,23 +431,41 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
-    // shadow and AO rays in separate CTAs when both exist and the launch is small enough for its tail to matter
-    // (LUZRT_RAY_PARTS=1 / 2 forces one / two CTAs per tile)
-    static const int parts_env = [] {
-        const char* e2 = getenv("LUZRT_RAY_PARTS");
-        return e2 ? atoi(e2) : 0;
+    // which ray kernel: the plain one (every ray of a pixel in one CTA) for the statistics variant and when forced by
+    // LUZRT_RAY_KERNEL=plain; otherwise the specialised bodies (split when both kinds of ray exist)
+    static const int kernel_env = [] { // 0 auto, 1 plain
+        const char* e2 = getenv("LUZRT_RAY_KERNEL");
+        return (e2 && e2[0] == 'p') ? 1 : 0;
+    }();
+    static const int one_visit_env = [] { // 0: the yielding node loop in the specialised kernels (tuning runs; the `if` form is 2-3 % faster there)
+        const char* e2 = getenv("LUZRT_ONE_VISIT");
+        return e2 ? atoi(e2) : -1;
     }();
     const bool any_shadow = args.fc.shadow_type == LUZW_SHADOW_RAYTRACING && args.fc.num_lights > 0;
-    const bool small = (size_t)args.rows.rows * args.rows.n_bands * 2 <= (size_t)args.fc.height; // a rank of >= 2
-    const bool split = !stats && any_shadow && args.fc.ao_num_samples > 0 && (parts_env == 2 || (parts_env == 0 && small));
+    const bool any_ao = args.fc.ao_num_samples > 0;
+    const bool plain = stats || kernel_env == 1 || (!any_shadow && !any_ao);
+    const bool split = !plain && any_shadow && any_ao;
     const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands * (split ? 2u : 1u));
-    static const int minb = [] { // resident CTAs per SM the ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
+    static const int minb = [] { // resident CTAs per SM the plain ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
         const char* e2 = getenv("LUZRT_LIGHT_MINB");
         return e2 ? atoi(e2) : 6;
     }();
-    if (split)
-        k_light_rays_split<6><<<grid, 128, smem, stream>>>(a2);
-    else if (stats)
+    if (split) {
+        if (one_visit_env == 0)
+            k_light_rays_split<false><<<grid, 128, smem, stream>>>(a2);
+        else
+            k_light_rays_split<true><<<grid, 128, smem, stream>>>(a2);
+    } else if (!plain && any_shadow) {
+        if (one_visit_env == 0)
+            k_light_rays_part<0, false><<<grid, 128, smem, stream>>>(a2);
+        else
+            k_light_rays_part<0, true><<<grid, 128, smem, stream>>>(a2);
+    } else if (!plain) {
+        if (one_visit_env == 0)
+            k_light_rays_part<1, false><<<grid, 128, smem, stream>>>(a2);
+        else
+            k_light_rays_part<1, true><<<grid, 128, smem, stream>>>(a2);
+    } else if (stats)
         k_light_rays<true, 4><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 4)
         k_light_rays<false, 4><<<grid, 128, smem, stream>>>(a2);
@@ -445,7 +473,7 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         k_light_rays<false, 5><<<grid, 128, smem, stream>>>(a2);
     else if (minb == 7)
         k_light_rays<false, 7><<<grid, 128, smem, stream>>>(a2);
-    else // 6 resident CTAs (80 registers) beat 4, 5, 7 and 8 on C3 / C4 / C2 taken together (profiles/r1_ab_split.md)
+    else
         k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;

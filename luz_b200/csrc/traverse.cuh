@@ -342,7 +342,11 @@ __device__ __forceinline__ int filter_candidates(const TraceScene& sc, const flo
 // (TLAS leaf order indices from collect_instances).  `stack` is LUZ_STACK_SIZE entries of caller storage.
 constexpr uint32_t kNoInstance = 0xFFFFFFFFu;
 
-template <bool CLOSEST, bool STATS, bool FACE_CULL = false>
+// ONE_VISIT: the node phase is a plain `if` (one node visit per pass of the loop) instead of the loop that yields
+// through sc.min_node_lanes.  Both forms visit one node per pass with the default min_node_lanes = 33, but the
+// compiler places the warp's re-join points differently, and which form is faster depends on the kernel around it
+// (profiles/r1_ab_onepass.md): the ray kernels pick per instantiation.
+template <bool CLOSEST, bool STATS, bool FACE_CULL = false, bool ONE_VISIT = false>
 __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo, const float3 wd, const float tmin,
                                           float tmax, HitInfo* hit, LocalStats* st, uint2* stack,
                                           const uint32_t* cand = nullptr, const int cand_stride = 0,
@@ -428,6 +432,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             tgroup = make_uint2(hdr.y, leaf_bits(slots & ~node_imask, hdr.z, hdr.w));
             // when only a few lanes are still descending, yield so that the lanes waiting at the end of this loop
             // (they hold primitives or need a pop) get served and everybody re-enters the node test together
+            if (ONE_VISIT) break;
             if (__popc(__activemask()) < (int)sc.min_node_lanes) break;
         }
 

@@ -10,7 +10,7 @@ for so in "$@"; do
     for c in ${AB_CONFIGS:-c3 c4 c2}; do
       steps=20; [ $c = c4 ] && steps=5
       echo "## $so $env $c" >> $OUT/${TAG}_ab.jsonl
-      env $env timeout 300 python bench.py --config $c --no-e2e --no-cpu-baseline --steps $steps --warmup 3 >> $OUT/${TAG}_ab.jsonl 2>> $OUT/${TAG}_ab.err
+      env $env timeout 300 python bench.py --config $c $AB_EXTRA --no-e2e --no-cpu-baseline --steps $steps --warmup 3 >> $OUT/${TAG}_ab.jsonl 2>> $OUT/${TAG}_ab.err
     done
   done
 done
