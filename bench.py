@@ -175,6 +175,18 @@ def run_ours(args):
     rt.light_pass(app.frame_count)
     st = rt.read(R.STATS)
     rt.set_debug(0)
+    if os.environ.get("LUZRT_TILE_OCCL") and rank == 0:
+        # diagnostic (stderr): how coherent shadow-ray occlusion is over the 8x4 pixel tile a warp traces
+        sm = rt.read(R.SHADOW_MASK)[..., 0]
+        lit = np.linalg.norm(rt.read(R.GBUF_NORMAL)[..., :3], axis=-1) > 0
+        hh, ww = (sm.shape[0] // 4) * 4, (sm.shape[1] // 8) * 8
+        tl = lit[:hh, :ww].reshape(hh // 4, 4, ww // 8, 8).sum(axis=(1, 3))
+        for l in range(min(int(app.scene_block().num_lights), 8)):
+            oc = (((sm >> l) & 1).astype(bool) & lit)[:hh, :ww].reshape(hh // 4, 4, ww // 8, 8).sum(axis=(1, 3))
+            t = tl > 0
+            sys.stderr.write("tile occlusion light %d: lit tiles %d, fully occluded %.3f, fully unoccluded %.3f, mixed %.3f, "
+                             "rays occluded %.3f\n" % (l, t.sum(), ((oc == tl) & t).sum() / t.sum(), ((oc == 0) & t).sum() / t.sum(),
+                                                        ((oc > 0) & (oc < tl)).sum() / t.sum(), oc.sum() / max(tl.sum(), 1)))
 
     for i in range(args.warmup):
         step(1 + i)
@@ -372,6 +384,7 @@ def run_ours(args):
                          "nodes_per_ray": nodes / max(rays_r, 1.0),
                          "tris_per_ray": tris / max(rays_r, 1.0),
                          "instances_per_ray": insts / max(rays_r, 1.0),
+                         "occluded_fraction": float(st.rays_occluded) / max(float(st.rays), 1.0),
                          "grays_per_s_per_gpu": rays_r / (light_ms * 1e6)},
             "roofline_l2": {"kernel": "light pass (k_light_rays + k_light_shade)", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
                             "peak": l2_gbs, "unit": "GB/s", "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None,

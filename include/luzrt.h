@@ -84,7 +84,8 @@ enum {
 enum {
     LUZRT_DEBUG_MASKS = 1, /* kept for ABI stability: the light pass always writes the per-ray visibility
                               bitmasks (they carry the rays' results to its shading kernel)            */
-    LUZRT_DEBUG_STATS = 2  /* light pass counts nodes / triangles / instances per ray */
+    LUZRT_DEBUG_STATS = 2, /* light pass counts nodes / triangles / instances per ray */
+    LUZRT_DEBUG_NO_HINTS = 4 /* shadow rays descend from the TLAS root without trying the tile's occluder hint first */
 };
 
 typedef struct luzrt_stats {

@@ -145,6 +145,8 @@ struct luzrt_ctx {
     size_t models_cap = 0;
 
     uint32_t *d_shadow_mask = nullptr, *d_ao_mask = nullptr;
+    uint32_t* d_hints = nullptr; // occluder hints of the shadow rays, [tile][light] (light_pass.cu)
+    size_t hints_cap = 0;
     size_t shadow_mask_words = 0, ao_mask_words = 0; // per pixel
     size_t shadow_mask_cap = 0, ao_mask_cap = 0;
     DeviceStats* d_stats = nullptr;
@@ -390,7 +392,7 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints};
     for (float* p : c->shadow_data)
         if (p) cudaFree(p);
     for (void* p : ptrs)
@@ -1028,6 +1030,17 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.stats = c->d_stats;
     a.lit_counters = c->d_lit;
     a.shadow_maps = c->d_shadow_recs;
+    a.hints = nullptr;
+    static const bool hints_env = [] { // LUZRT_SHADOW_HINTS=0: no occluder hints (tuning / A-B runs)
+        const char* e = getenv("LUZRT_SHADOW_HINTS");
+        return !(e && e[0] == '0');
+    }();
+    if (hints_env && !(c->debug & LUZRT_DEBUG_NO_HINTS) && c->fc.shadow_type == LUZW_SHADOW_RAYTRACING && c->fc.num_lights > 0) {
+        const size_t tiles = (size_t)((c->w + 15) / 16) * ((a.rows.rows + 7) / 8) * a.rows.n_bands;
+        int rc;
+        if ((rc = grow(c, c->d_hints, c->hints_cap, tiles * (size_t)c->fc.num_lights)) != LUZRT_OK) return rc;
+        a.hints = c->d_hints;
+    }
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
     CU(c, wait_gather(c, a.out));
@@ -1038,7 +1051,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     CU(c, cudaEventRecord(c->ev[EV_LIGHT_RAYS][0], c->stream));
     CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1]));
     c->ev_valid[EV_LIGHT_RAYS] = true;
-    c->launches += 2;
+    c->launches += a.hints ? 3 : 2;
     ev_end(c, EV_LIGHT);
     return LUZRT_OK;
 }

@@ -339,7 +339,10 @@ __device__ __forceinline__ int filter_candidates(const TraceScene& sc, const flo
 // CLOSEST == false: any-hit, returns true at the first committed intersection.
 // CLOSEST == true : returns true if something was hit; *hit describes the nearest one.
 // n_cand < 0: descend from the TLAS root.  n_cand >= 0: visit only the instances cand[k * cand_stride]
-// (TLAS leaf order indices from collect_instances).  `stack` is LUZ_STACK_SIZE entries of caller storage.
+// (TLAS leaf order indices from collect_instances); with then_root the candidates are only tried FIRST (occluder
+// hints of shadow rays: an any-hit result does not depend on the order) and the root descent follows if none of
+// them is hit.  Any-hit calls may pass `hit` to learn the instance that was hit (hit->inst).
+// `stack` is LUZ_STACK_SIZE entries of caller storage.
 constexpr uint32_t kNoInstance = 0xFFFFFFFFu;
 
 // ONE_VISIT: the node phase is a plain `if` (one node visit per pass of the loop) instead of the loop that yields
@@ -350,7 +353,7 @@ template <bool CLOSEST, bool STATS, bool FACE_CULL = false, bool ONE_VISIT = fal
 __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo, const float3 wd, const float tmin,
                                           float tmax, HitInfo* hit, LocalStats* st, uint2* stack,
                                           const uint32_t* cand = nullptr, const int cand_stride = 0,
-                                          const int n_cand = -1) {
+                                          const int n_cand = -1, const bool then_root = false) {
     // rays with NaNs (e.g. the vertical-light tangent of light.frag:90) and null directions miss
     if (!(wo.x == wo.x && wo.y == wo.y && wo.z == wo.z && wd.x == wd.x && wd.y == wd.y && wd.z == wd.z &&
           tmin == tmin && tmax == tmax))
@@ -360,7 +363,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     int sp = 0;
     int inst_sp = -1; // stack height at which the current instance was entered, -1 = in the TLAS
     uint32_t cur_inst = 0;
-    const bool from_root = n_cand < 0;
+    bool from_root = n_cand < 0;
 
     float3 o = wo, d = wd;
     RaySpace rs;
@@ -458,7 +461,10 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                         const float3 n = f3(q.mv.w, q.ev.w, q.mw.w); // (p1 - p0) x (p2 - p0)
                         if (!(face_sign * dot3(d, n) > 0.0f)) continue;
                     }
-                    if (!CLOSEST) return true;
+                    if (!CLOSEST) {
+                        if (hit) hit->inst = cur_inst;
+                        return true;
+                    }
                     tmax = t;
                     found = true;
                     hit->t = t;
@@ -503,6 +509,15 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                     }
                 }
                 if (pending != kNoInstance) continue;
+                if (then_root && !from_root) { // none of the hinted instances was hit: the ordinary descent
+                    from_root = true;
+                    o = wo;
+                    d = wd;
+                    rs = make_ray_space(o, d);
+                    nodes = sc.tlas_nodes;
+                    ngroup = make_uint2(0u, 0x80000000u);
+                    continue;
+                }
                 break;
             }
             const uint2 e = stack[--sp];

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libluzrt.so")
 # luzrt_read selectors
 IMG_LIGHT, IMG_HISTORY, SHADOW_MASK, AO_MASK, STATS = 0, 1, 2, 3, 4
 GBUF_ALBEDO, GBUF_NORMAL, GBUF_MATERIAL, GBUF_EMISSION, GBUF_DEPTH, IMG_COMPOSE, TIMINGS = 5, 6, 7, 8, 9, 10, 11
-DEBUG_MASKS, DEBUG_STATS = 1, 2
+DEBUG_MASKS, DEBUG_STATS, DEBUG_NO_HINTS = 1, 2, 4
 
 EXPORTS = [
     "luzrt_create", "luzrt_destroy", "luzrt_last_error", "luzrt_version", "luzrt_comm_unique_id",

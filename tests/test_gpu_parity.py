@@ -309,6 +309,39 @@ def test_ao_candidate_lists_match_exhaustive(rt_factory):
         rt.close()
 
 
+def test_shadow_hints_do_not_change_visibility(rt_factory):
+    """Occluder hints (k_shadow_hints, light_pass.cu): one ray per 16x8 tile and light finds an occluding instance that
+    the tile's shadow rays try before the TLAS descent.  Any-hit visibility does not depend on the order of the
+    tests: masks and image must be bit-identical with LUZRT_DEBUG_NO_HINTS, for the statistics variant and the
+    product kernels, also with several samples per light and more than 64 lights."""
+    w, h = 320, 180
+    bn = S.blue_noise()
+    for n_lights, samples, grid in ((4, 1, 6), (3, 3, 4)):
+        sc = S.synthetic_scene(w, h, grid=grid, n_lights=n_lights, light_samples=samples, ao_samples=2, eye=(7, 3.0, 9))
+        rt = rt_factory()
+        rt.resize(w, h)
+        rt.set_blue_noise(bn)
+        S.make_rt_scene(rt, sc)
+        rt.set_scene(sc["scene"])
+        rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+        res = {}
+        for flags in (R.DEBUG_NO_HINTS, 0, R.DEBUG_STATS | R.DEBUG_NO_HINTS, R.DEBUG_STATS):
+            rt.set_debug(flags)
+            rt.light_pass(11)
+            res[flags] = (rt.read(R.SHADOW_MASK), rt.read(R.AO_MASK), rt.read(R.IMG_LIGHT))
+        st_hint = rt.read(R.STATS)
+        ref = res[R.DEBUG_NO_HINTS]
+        assert np.unpackbits(ref[0].view(np.uint8)).sum() > 1000  # the scene does have shadows
+        for flags, got in res.items():
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]), flags
+            assert np.array_equal(got[2], ref[2], equal_nan=True), flags
+        rt.set_debug(R.DEBUG_STATS | R.DEBUG_NO_HINTS)
+        rt.light_pass(11)
+        st_plain = rt.read(R.STATS)
+        assert st_hint.rays == st_plain.rays and st_hint.rays_occluded == st_plain.rays_occluded
+        rt.close()
+
+
 def test_tlas_refit_matches_rebuild(rt_factory):
     rt = rt_factory()
     w, h = 256, 144
