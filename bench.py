@@ -371,8 +371,8 @@ def run_ours(args):
             # L1/L2 resident, so the same algorithmic bytes are also shown against the L2 read bandwidth probed in
             # this run (roofline_l2).  traffic = ncu dram bytes per launch of the committed profile, when it is for
             # this workload.
-            "roofline": {"kernel": "light pass = k_light_rays (ray generation + any-hit traversal, the dominant kernel) + "
-                                   "k_light_shade (Cook-Torrance), timed together", "bound": "hbm",
+            "roofline": {"kernel": "light pass = k_shadow_hints + k_light_rays_split (ray generation + any-hit traversal, the dominant "
+                                   "kernel) + k_light_shade (Cook-Torrance), timed together", "bound": "hbm",
                          "achieved": light_bytes / (light_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
                          "frac": light_bytes / (light_ms * 1e6) / hbm_peak, "traffic": ncu_traffic(args, "light_pass"),
                          "peak_source": hbm_src,
@@ -386,7 +386,7 @@ def run_ours(args):
                          "instances_per_ray": insts / max(rays_r, 1.0),
                          "occluded_fraction": float(st.rays_occluded) / max(float(st.rays), 1.0),
                          "grays_per_s_per_gpu": rays_r / (light_ms * 1e6)},
-            "roofline_l2": {"kernel": "light pass (k_light_rays + k_light_shade)", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
+            "roofline_l2": {"kernel": "light pass (k_shadow_hints + k_light_rays_split + k_light_shade)", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
                             "peak": l2_gbs, "unit": "GB/s", "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None,
                             "peak_source": "luzrt_probe_read_bandwidth, 32 MiB resident buffer, measured in this run"},
             "roofline_taa": {"kernel": "k_taa", "bound": "hbm", "achieved": 52.0 * own_px / (taa_ms * 1e6),
