@@ -1,9 +1,16 @@
-// light_pass.cu -- the deferred lighting pass as two kernels: k_light_rays fires every shadow and AO ray of
-// light.frag and leaves one bit per ray (1 = occluded) in the per-pixel visibility masks (all ray state in
-// registers, no ray buffers in HBM); k_light_shade evaluates light.frag:171-235 with the occluded fractions read
-// back from those bits.
+// light_pass.cu -- the deferred lighting pass.  Ray kernels fire every shadow and AO ray of light.frag and leave one bit
+// per ray (1 = occluded) in the per-pixel visibility masks (all ray state in registers, no ray buffers in HBM);
+// k_light_shade evaluates light.frag:171-235 with the occluded fractions read back from those bits.
 //
-// Why two kernels: a single fused kernel (this file up to commit "Host path: read-back in flight ...") keeps the whole
+//   k_shadow_hints        one ray per 16x8 tile and light: an occluding instance the tile's shadow rays try first
+//   k_light_rays_split    two CTAs per tile: part 0 the shadow rays, part 1 the AO rays (frames that have both)
+//   k_light_rays_part<P>  frames with one kind of ray (C4: shadow rays only; shadowType == ShadowMap: AO rays only)
+//   k_light_rays          every ray of a pixel in one CTA: the LUZRT_DEBUG_STATS variant (counts nodes / triangles /
+//                         instances) and the A/B baseline
+//   k_light_shade         Cook-Torrance over the lights, shadow factors and AO from the masks
+// All ray kernels instantiate one body (light_rays_body) and produce identical bits (tests/test_gpu_parity.py run_light).
+//
+// Why rays and shading are separate kernels: a single fused kernel (this file up to commit "Host path: read-back in flight ...") keeps the whole
 // BRDF state of the pixel alive inside the traversal loop (albedo, F0, V, Lo, roughness ... ~30 registers) next to
 // ~45 registers of traversal state, which at the occupancy that hides the traversal's latencies best (80 registers,
 // 6 CTAs of 128 threads per SM) is spilled to local memory inside the hottest loop.  The ray kernel only carries what
