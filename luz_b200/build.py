@@ -31,7 +31,7 @@ CU_SOURCES = ["api.cu", "bvh_build.cu", "light_pass.cu", "taa.cu", "gbuffer.cu",
 # built with -fmad=false so that implicit contraction cannot change results (ill-conditioned BRDF terms
 # amplify it), and use explicit fmaf() only where rounding is not part of parity (box tests).
 NO_FMAD = {"light_pass.cu", "taa.cu", "gbuffer.cu", "volumetric.cu", "shadow_map.cu"}
-HOST_SOURCES = ["json.cpp", "scene.cpp", "gpu_scene.cpp", "capi.cpp"]
+HOST_SOURCES = ["json.cpp", "scene.cpp", "gpu_scene.cpp", "capi.cpp", "import.cpp", "png.cpp"]
 
 
 def _newer(target, deps):

@@ -31,6 +31,8 @@ def load_library():
         "luzhost_last_error": (C.c_char_p, [vp]),
         "luzhost_load_project": (i32, [vp, C.c_char_p, C.c_char_p]),
         "luzhost_save_project": (i32, [vp, C.c_char_p, C.c_char_p]),
+        "luzhost_import": (i32, [vp, C.c_char_p, i32]),
+        "luzhost_import_dump": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, u32]),
         "luzhost_set_extent": (i32, [vp, u32, u32, i32]),
         "luzhost_add_assets": (i32, [vp]),
         "luzhost_update_resources": (i32, [vp]),
@@ -110,6 +112,10 @@ class LuzHost:
 
     def load_project(self, path, bin_path):
         self._ck(self.lib.luzhost_load_project(self.h, path.encode(), bin_path.encode()))
+
+    def import_file(self, path, as_scene=True):
+        """AssetIO::Import of a .glb / .gltf / .obj scene or a .png texture (luz_b200/host/import.cpp)."""
+        self._ck(self.lib.luzhost_import(self.h, path.encode(), 1 if as_scene else 0))
 
     def save_project(self, path, bin_path):
         self._ck(self.lib.luzhost_save_project(self.h, path.encode(), bin_path.encode()))

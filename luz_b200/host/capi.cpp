@@ -1,10 +1,12 @@
 // capi.cpp -- flat C interface over the host mirror, for harnesses that cannot include C++ headers
 // (the Python tests / bench.py).  A C++ Luz host uses gpu_scene.hpp / scene.hpp directly.
 // The frame loop is main.cpp's RenderFrame (source/Core/main.cpp:223-311) restricted to this path.
+#include <cstdio>
 #include <cstring>
 #include <string>
 
 #include "gpu_scene.hpp"
+#include "import.hpp"
 
 using namespace luzhost;
 
@@ -68,6 +70,38 @@ LUZHOST_API int luzhost_load_project(luzhost_app* a, const char* path, const cha
     if (!a->scene) return fail(a, -1, "initialScene not found");
     a->camera = a->assets.GetMainCamera(a->scene);
     refresh_lists(a);
+    return 0;
+}
+// == AssetIO::Import (AssetIO.cpp:73-82) as the editor's drag-and-drop does it (Editor::AssetsPanel): the file's
+// assets join the manager.  as_scene != 0 also makes the imported scene the one being rendered (its nodes are what
+// GPUScene flattens); otherwise its top-level nodes are added to the current scene, like dropping a model into it.
+LUZHOST_API int luzhost_import(luzhost_app* a, const char* path, int as_scene) {
+    a->assets.error.clear();
+    const UUID id = AssetIO::Import(path, a->assets);
+    if (!id) return fail(a, -1, a->assets.error.empty() ? std::string("nothing to import from ") + path : a->assets.error);
+    Ref<SceneAsset> imported = a->assets.Get<SceneAsset>(id);
+    if (!imported) return 0; // a texture
+    if (as_scene || !a->scene) {
+        a->scene = imported;
+        a->assets.initialScene = id;
+        a->camera = a->assets.GetMainCamera(a->scene);
+    } else {
+        for (auto& n : imported->nodes) a->scene->Add(n);
+    }
+    refresh_lists(a);
+    return 0;
+}
+// Test hook: import `path` into a fresh manager and write what was imported in the JSON layout of oracle/ref_import.cpp.
+LUZHOST_API int luzhost_import_dump(const char* path, const char* out_json, char* err, uint32_t err_cap) {
+    AssetManager m;
+    const UUID id = AssetIO::Import(path, m);
+    if (err && err_cap) snprintf(err, err_cap, "%s", m.error.c_str());
+    if (!id) return -1;
+    const std::string text = AssetIO::DumpImportedScene(m, id);
+    FILE* f = fopen(out_json, "w");
+    if (!f) return -2;
+    fwrite(text.data(), 1, text.size(), f);
+    fclose(f);
     return 0;
 }
 LUZHOST_API int luzhost_save_project(luzhost_app* a, const char* path, const char* bin_path) {

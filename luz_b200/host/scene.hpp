@@ -2,8 +2,8 @@
 //
 // Mirrors (same names, fields, defaults and (de)serialisation keys) the reference's
 // source/Resources/AssetManager.hpp:14-353 and Serializer.hpp:65-158, written from scratch on top of
-// lmath.hpp / ljson.hpp instead of glm / nlohmann.  Everything editor-related (ImGui, cloning,
-// import of glTF/OBJ) is out of scope.
+// lmath.hpp / ljson.hpp instead of glm / nlohmann.  Scene import (glTF / GLB / OBJ / PNG) is import.hpp; everything
+// editor-related (ImGui, cloning) is out of scope.
 #pragma once
 
 #include <cstdint>
