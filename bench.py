@@ -112,6 +112,56 @@ def blue_noise(scenes):
     return scenes.synthetic_blue_noise(1024)
 
 
+def sysfs_bus_id(smi_csv, index):
+    """PCI address of GPU `index` as sysfs spells it, from `nvidia-smi --query-gpu=index,pci.bus_id --format=csv,noheader`
+    (nvidia-smi prints an 8-digit PCI domain and upper case, sysfs a 4-digit one and lower case)."""
+    for line in smi_csv.splitlines():
+        parts = [t.strip() for t in line.split(",")]
+        if len(parts) >= 2 and parts[0].isdigit() and int(parts[0]) == index:
+            bus = parts[1].lower()
+            return bus[4:] if len(bus.split(":")[0]) == 8 else bus
+    return None
+
+
+def cpulist_to_set(text):
+    """'0-3,8,10-11' -> {0,1,2,3,8,10,11} (the format of /sys/devices/system/node/nodeN/cpulist)."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local):
+    """Multi-GPU runs: keep this rank's threads (and so the page-locked buffers it first touches) on the NUMA node its GPU
+    hangs off.  Eight ranks staging 50 MB per step each through buffers on one socket is what bounds the end-to-end
+    number at 8 GPUs (profiles/r1_scaling.md).  Best effort: any failure leaves the affinity alone.  Returns a note for
+    the JSON line.  LUZ_BENCH_NO_NUMA=1 disables it."""
+    if os.environ.get("LUZ_BENCH_NO_NUMA"):
+        return "disabled"
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=index,pci.bus_id", "--format=csv,noheader"], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local]) if visible and all(t.strip().isdigit() for t in visible.split(",")) else local
+        bus = sysfs_bus_id(out, index)
+        if bus is None:
+            return "gpu not listed"
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "no NUMA information"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = cpulist_to_set(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return "no allowed CPU on node %d" % node
+        os.sched_setaffinity(0, cpus)
+        return "node %d (%d CPUs)" % (node, len(cpus))
+    except Exception as e:  # noqa: BLE001 -- never fail the bench over placement
+        return "unavailable (%s)" % type(e).__name__
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -129,6 +179,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         sys.exit("bench.py: no CUDA device; the lighting path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_note = bind_to_gpu_numa_node(local) if world > 1 else "single GPU: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -400,7 +451,8 @@ def run_ours(args):
                                   "wall clock over %d steps incl. pipeline fill and drain" % e2e["n_pipe"],
                           "serial_ms_per_step": e2e["serial_ms"],
                           "kernels_ms_under_copies": {"light": e2e["light_ms"], "taa": e2e["taa_ms"]},
-                          "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"])}
+                          "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
+                          "host_numa_binding": numa_note}
         if cpu_base:
             out["cpu_baseline"] = cpu_base
         print(json.dumps(out), flush=True)
