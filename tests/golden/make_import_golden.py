@@ -4,7 +4,7 @@ OWN importers make of them (oracle/_ref/ref_import = source/Resources/AssetIO.cp
 stb_image, compiled in place).  Run in the build container only (needs /root/reference); the committed files are what
 tests/test_host_import.py uses.
 
- - cube.glb, point.obj, directional.obj : the reference's own data assets (assets/), verbatim
+ - cube.glb.gz, point.obj.gz, directional.obj.gz : the reference's own data assets (assets/), gzip'ed
  - multi.gltf + multi.bin, embedded.gltf, shapes.obj + shapes.mtl + checker8.png : written by this script to reach
    the branches the reference's assets do not (interleaved views, u8 / u32 indices, supplied tangents, missing
    normals / uvs, node TRS / matrix / light extension, two scenes, data URIs, quads, polygons, negative indices,
@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "import")
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("LUZ_REFERENCE", "/root/reference")
+REFERENCE_ASSETS = ("cube.glb", "point.obj", "directional.obj")
 
 
 def png_rgb(w, h, pixel):
@@ -213,16 +214,20 @@ def main():
         sys.exit("reference not mounted at %s" % REF)
     os.makedirs(OUT, exist_ok=True)
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "_ref/ref_import"])
-    for name in ("cube.glb", "point.obj", "directional.obj"):
-        shutil.copyfile(os.path.join(REF, "assets", name), os.path.join(OUT, name))
+    for name in REFERENCE_ASSETS:  # data assets of the reference, stored gzip'ed like tests/golden/default.luzbin.gz
+        with open(os.path.join(REF, "assets", name), "rb") as f:
+            data = f.read()
+        with open(os.path.join(OUT, name + ".gz"), "wb") as f:
+            f.write(gzip.compress(data, 9, mtime=0))
     write_gltf_assets()
     write_obj_assets()
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_import")
     env = dict(os.environ, MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
     with tempfile.TemporaryDirectory() as tmp:
-        for name in ("cube.glb", "point.obj", "directional.obj", "multi.gltf", "embedded.gltf", "shapes.obj"):
+        for name in REFERENCE_ASSETS + ("multi.gltf", "embedded.gltf", "shapes.obj"):
             out = os.path.join(tmp, "out.json")
-            subprocess.check_call([exe, os.path.join(OUT, name), out], cwd=tmp, env=env, stdout=subprocess.DEVNULL)
+            src = os.path.join(REF, "assets", name) if name in REFERENCE_ASSETS else os.path.join(OUT, name)
+            subprocess.check_call([exe, src, out], cwd=tmp, env=env, stdout=subprocess.DEVNULL)
             with open(out, "rb") as f:
                 text = f.read()
             json.loads(text)

@@ -20,6 +20,17 @@ ASSETS = os.path.join(HERE, "golden", "import")
 FILES = ["cube.glb", "point.obj", "directional.obj", "multi.gltf", "embedded.gltf", "shapes.obj"]
 
 
+def asset_path(name, tmp_path):
+    """Path of a scene file; the reference's own assets are stored gzip'ed and unpacked next to nothing else."""
+    p = os.path.join(ASSETS, name)
+    if os.path.exists(p):
+        return p
+    out = tmp_path / name
+    with gzip.open(p + ".gz", "rb") as f:
+        out.write_bytes(f.read())
+    return str(out)
+
+
 def import_dump(path, tmp_path):
     lib = host.load_library()
     err = C.create_string_buffer(512)
@@ -53,7 +64,7 @@ def assert_same(got, ref, where=""):
 def test_import_matches_reference_importer(name, tmp_path):
     with gzip.open(os.path.join(ASSETS, name + ".json.gz"), "rt") as f:
         ref = json.load(f)
-    got = import_dump(os.path.join(ASSETS, name), tmp_path)
+    got = import_dump(asset_path(name, tmp_path), tmp_path)
     assert_same(got, ref)
 
 
@@ -107,7 +118,7 @@ def test_imported_scene_flattens_like_a_loaded_project(tmp_path):
     instance of the 24-vertex cube with the material's checker texture bound, and it survives SaveProject ->
     LoadProject."""
     app = host.LuzHost(None)
-    app.import_file(os.path.join(ASSETS, "cube.glb"), as_scene=True)
+    app.import_file(asset_path("cube.glb", tmp_path), as_scene=True)
     app.set_extent(320, 180, create_images=False)
     app.add_assets()
     app.update_resources()
