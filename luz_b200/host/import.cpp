@@ -713,9 +713,17 @@ UUID ImportSceneGLTF(const std::string& path, AssetManager& manager) {
             return 0;
         }
         loadedTextures[i] = create<TextureAsset>(manager, ObjectType::TextureAsset, str_or(tex, "name", ""));
-        if (!decode_texture_bytes(bytes, loadedTextures[i], err)) {
+        std::vector<uint16_t> deep;
+        Ref<TextureAsset>& t = loadedTextures[i];
+        if (!decode_png(bytes.data(), bytes.size(), t->data, t->width, t->height, err, &deep)) {
             manager.error = "glTF image " + std::to_string(i) + ": " + err + " (only PNG is decoded)";
             return 0;
+        }
+        t->channels = 4;
+        if (!deep.empty()) {
+            // tiny_gltf hands 16-bit PNGs over as 16-bit samples and the reference copies the first width * height * 4
+            // BYTES of them (AssetIO.cpp:150-163), i.e. the first half of the image as little-endian u16: mirrored
+            memcpy(t->data.data(), deep.data(), t->data.size());
         }
     }
     auto texture_of = [&](const lj::Value& holder, const char* key) -> Ref<TextureAsset> {

@@ -181,7 +181,8 @@ bool inflate_zlib(const uint8_t* data, size_t size, std::vector<uint8_t>& out, s
     return true;
 }
 
-bool decode_png(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, std::string& err) {
+bool decode_png(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, std::string& err,
+                std::vector<uint16_t>* deep) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (size < 8 || memcmp(data, sig, 8) != 0) { err = "not a PNG"; return false; }
     size_t off = 8;
@@ -227,8 +228,7 @@ bool decode_png(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, in
         off += 12 + (size_t)len;
     }
     if (!w || !h || ctype < 0) { err = "missing IHDR"; return false; }
-    if (interlace) { err = "interlaced PNG is not supported"; return false; }
-    if (depth > 8) { err = "16-bit PNG is not supported"; return false; }
+    if (interlace > 1) { err = "bad interlace method"; return false; }
     int channels;
     switch (ctype) {
         case 0: channels = 1; break;
@@ -238,70 +238,107 @@ bool decode_png(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, in
         case 6: channels = 4; break;
         default: err = "bad colour type"; return false;
     }
-    if ((ctype == 2 || ctype == 4 || ctype == 6) && depth != 8) { err = "bad bit depth"; return false; }
-    if (depth != 1 && depth != 2 && depth != 4 && depth != 8) { err = "bad bit depth"; return false; }
+    if ((ctype == 2 || ctype == 4 || ctype == 6) && depth != 8 && depth != 16) { err = "bad bit depth"; return false; }
+    if (ctype == 3 && depth == 16) { err = "bad bit depth"; return false; }
+    if (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16) { err = "bad bit depth"; return false; }
     if ((uint64_t)w * h > (1ull << 28)) { err = "image too large"; return false; }
     std::vector<uint8_t> raw;
     raw.reserve(((size_t)w * channels * depth / 8 + 2) * h);
     if (!inflate_zlib(idat.data(), idat.size(), raw, err)) return false;
-    const size_t bpp = (size_t)((channels * depth + 7) / 8), stride = ((size_t)w * channels * depth + 7) / 8;
-    if (raw.size() < (stride + 1) * h) { err = "not enough image data"; return false; }
-    // unfilter in place
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
-    std::vector<uint8_t> pix((size_t)stride * h);
-    for (uint32_t y = 0; y < h; y++) {
-        const uint8_t* row = raw.data() + (stride + 1) * y;
-        const int filter = row[0];
-        memcpy(cur.data(), row + 1, stride);
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-            int v = cur[i];
-            switch (filter) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: v += paeth(a, b, c); break;
-                default: err = "bad filter type"; return false;
-            }
-            cur[i] = (uint8_t)v;
-        }
-        memcpy(pix.data() + stride * y, cur.data(), stride);
-        prev.swap(cur);
-    }
-    // expand to RGBA8 the way stb_image does when asked for 4 channels
+    const size_t bpp = (size_t)((channels * depth + 7) / 8);
     rgba.assign((size_t)w * h * 4, 255);
+    if (deep) deep->clear();
+    if (deep && depth == 16) deep->assign((size_t)w * h * 4, 0xFFFF);
     static const int scale_table[9] = {0, 0xff, 0x55, 0, 0x11, 0, 0, 0, 0x01};
-    for (uint32_t y = 0; y < h; y++) {
-        const uint8_t* row = pix.data() + stride * y;
-        uint8_t* o = rgba.data() + (size_t)y * w * 4;
-        for (uint32_t x = 0; x < w; x++, o += 4) {
-            if (ctype == 0 || ctype == 3) {
-                int v;
-                if (depth == 8) {
-                    v = row[x];
-                } else {
-                    const int per = 8 / depth, shift = (per - 1 - (int)(x % per)) * depth;
-                    v = (row[x / per] >> shift) & ((1 << depth) - 1);
+
+    // one (sub)image of pw x ph pixels starting at raw[pos]: unfilter, then scatter its pixels to (x0 + x*dx, y0 + y*dy)
+    auto decode_pass = [&](size_t& pos, uint32_t pw, uint32_t ph, uint32_t x0, uint32_t y0, uint32_t dx, uint32_t dy) -> bool {
+        if (!pw || !ph) return true;
+        const size_t stride = ((size_t)pw * channels * depth + 7) / 8;
+        if (raw.size() < pos + (stride + 1) * ph) { err = "not enough image data"; return false; }
+        std::vector<uint8_t> prev(stride, 0), cur(stride);
+        for (uint32_t y = 0; y < ph; y++) {
+            const uint8_t* row = raw.data() + pos + (stride + 1) * y;
+            const int filter = row[0];
+            memcpy(cur.data(), row + 1, stride);
+            for (size_t i = 0; i < stride; i++) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int v = cur[i];
+                switch (filter) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: v += paeth(a, b, c); break;
+                    default: err = "bad filter type"; return false;
                 }
-                if (ctype == 3) {
-                    if (v >= pal_n && v >= 256) v = 0;
-                    o[0] = pal[v][0], o[1] = pal[v][1], o[2] = pal[v][2], o[3] = pal[v][3];
-                } else {
-                    const bool transparent = has_key && v == key[0];
-                    const int g = v * scale_table[depth];
-                    o[0] = o[1] = o[2] = (uint8_t)g;
-                    o[3] = transparent ? 0 : 255;
-                }
-            } else if (ctype == 2) {
-                o[0] = row[3 * x], o[1] = row[3 * x + 1], o[2] = row[3 * x + 2];
-                o[3] = (has_key && o[0] == key[0] && o[1] == key[1] && o[2] == key[2]) ? 0 : 255;
-            } else if (ctype == 4) {
-                o[0] = o[1] = o[2] = row[2 * x];
-                o[3] = row[2 * x + 1];
-            } else {
-                memcpy(o, row + 4 * x, 4);
+                cur[i] = (uint8_t)v;
             }
+            // expand to RGBA8 the way stb_image does when asked for 4 channels of 8 bits: 16-bit samples keep their
+            // high byte, the tRNS colour key is compared at full depth, sub-byte grey is scaled to 0..255
+            const uint8_t* r = cur.data();
+            for (uint32_t x = 0; x < pw; x++) {
+                uint8_t* o = rgba.data() + ((size_t)(y0 + y * dy) * w + (x0 + x * dx)) * 4;
+                auto sample = [&](size_t k) -> uint32_t { // k-th sample of the row at full depth (8 or 16 bit)
+                    return depth == 16 ? (uint32_t)((r[2 * k] << 8) | r[2 * k + 1]) : r[k];
+                };
+                auto to8 = [&](uint32_t v) -> uint8_t { return (uint8_t)(depth == 16 ? (v >> 8) : v); };
+                if (ctype == 0 || ctype == 3) {
+                    uint32_t v;
+                    if (depth >= 8) {
+                        v = sample(x);
+                    } else {
+                        const int per = 8 / depth, shift = (per - 1 - (int)(x % per)) * depth;
+                        v = (uint32_t)(r[x / per] >> shift) & ((1u << depth) - 1u);
+                    }
+                    if (ctype == 3) {
+                        o[0] = pal[v & 255][0], o[1] = pal[v & 255][1], o[2] = pal[v & 255][2], o[3] = pal[v & 255][3];
+                    } else {
+                        const bool transparent = has_key && v == key[0];
+                        o[0] = o[1] = o[2] = depth < 8 ? (uint8_t)(v * scale_table[depth]) : to8(v);
+                        o[3] = transparent ? 0 : 255;
+                    }
+                } else if (ctype == 2) {
+                    const uint32_t R = sample(3 * x), G = sample(3 * x + 1), B = sample(3 * x + 2);
+                    o[0] = to8(R), o[1] = to8(G), o[2] = to8(B);
+                    o[3] = (has_key && R == key[0] && G == key[1] && B == key[2]) ? 0 : 255;
+                } else if (ctype == 4) {
+                    o[0] = o[1] = o[2] = to8(sample(2 * x));
+                    o[3] = to8(sample(2 * x + 1));
+                } else {
+                    for (int k = 0; k < 4; k++) o[k] = to8(sample(4 * x + k));
+                }
+                if (deep && depth == 16) { // the same pixel at full depth (stb's 16-bit API)
+                    uint16_t* q = deep->data() + ((size_t)(y0 + y * dy) * w + (x0 + x * dx)) * 4;
+                    if (ctype == 0) {
+                        q[0] = q[1] = q[2] = (uint16_t)sample(x);
+                        q[3] = (has_key && sample(x) == key[0]) ? 0 : 0xFFFF;
+                    } else if (ctype == 2) {
+                        for (int k = 0; k < 3; k++) q[k] = (uint16_t)sample(3 * x + k);
+                        q[3] = o[3] ? 0xFFFF : 0;
+                    } else if (ctype == 4) {
+                        q[0] = q[1] = q[2] = (uint16_t)sample(2 * x);
+                        q[3] = (uint16_t)sample(2 * x + 1);
+                    } else {
+                        for (int k = 0; k < 4; k++) q[k] = (uint16_t)sample(4 * x + k);
+                    }
+                }
+            }
+            prev.swap(cur);
+        }
+        pos += (stride + 1) * ph;
+        return true;
+    };
+    size_t pos = 0;
+    if (!interlace) {
+        if (!decode_pass(pos, w, h, 0, 0, 1, 1)) return false;
+    } else { // Adam7: seven reduced images, each filtered on its own
+        static const uint32_t xs[7] = {0, 4, 0, 2, 0, 1, 0}, ys[7] = {0, 0, 4, 0, 2, 0, 1};
+        static const uint32_t dxs[7] = {8, 8, 4, 4, 2, 2, 1}, dys[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int p = 0; p < 7; p++) {
+            const uint32_t pw = (w > xs[p]) ? (w - xs[p] + dxs[p] - 1) / dxs[p] : 0;
+            const uint32_t ph = (h > ys[p]) ? (h - ys[p] + dys[p] - 1) / dys[p] : 0;
+            if (!decode_pass(pos, pw, ph, xs[p], ys[p], dxs[p], dys[p])) return false;
         }
     }
     width = (int)w;

@@ -5,10 +5,10 @@ stb_image, compiled in place).  Run in the build container only (needs /root/ref
 tests/test_host_import.py uses.
 
  - cube.glb.gz, point.obj.gz, directional.obj.gz : the reference's own data assets (assets/), gzip'ed
- - multi.gltf + multi.bin, embedded.gltf, shapes.obj + shapes.mtl + checker8.png : written by this script to reach
+ - multi.gltf + multi.bin, embedded.gltf, shapes.obj + shapes.mtl + checker8.png / deep16.png / adam7.png : written by this script to reach
    the branches the reference's assets do not (interleaved views, u8 / u32 indices, supplied tangents, missing
    normals / uvs, node TRS / matrix / light extension, two scenes, data URIs, quads, polygons, negative indices,
-   per-face materials, .mtl fields, textures)
+   per-face materials, .mtl fields, textures incl. 16-bit and interlaced PNG)
  - *.json.gz : ref_import's dump of each (floats as bit patterns).  The reference accumulates tangents into
    `new glm::vec3[...]` without initialising it (AssetIO.cpp:314-315), so its output depends on stale heap contents;
    the goldens are produced with MALLOC_PERTURB_=255 and GLIBC_TUNABLES=glibc.malloc.tcache_count=0 (glibc then hands
@@ -31,6 +31,34 @@ def png_rgb(w, h, pixel):
     return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(raw, 9)) + chunk(b"IEND", b"")
 
 
+def png_raw(w, h, depth, ctype, rows, interlace=0):
+    raw = b"".join(b"\x00" + r for r in rows)
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace)) + \
+        chunk(b"IDAT", zlib.compress(raw, 9)) + chunk(b"IEND", b"")
+
+
+def png_rgba16(w, h):
+    """16 bits per sample: stb's 8-bit API keeps the high byte."""
+    rows = [b"".join(struct.pack(">4H", (x * 4099 + y * 257) & 0xFFFF, (x * 1543 + y * 7919) & 0xFFFF, (x * y * 911) & 0xFFFF,
+                                 65535 - ((x + y) * 3001 & 0xFFFF)) for x in range(w)) for y in range(h)]
+    return png_raw(w, h, 16, 6, rows)
+
+
+def png_adam7_rgb(w, h):
+    """Adam7-interlaced RGB8: seven reduced images, each with its own scanlines."""
+    px = [[((x * 37 + y * 11) & 255, (x * 5 + y * 83) & 255, (x * y * 7 + 13) & 255) for x in range(w)] for y in range(h)]
+    xs, ys, dxs, dys = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1], [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+    rows = []
+    for p in range(7):
+        for y in range(ys[p], h, dys[p]):
+            r = b"".join(bytes(px[y][x]) for x in range(xs[p], w, dxs[p]))
+            if r:
+                rows.append(r)
+    return png_raw(w, h, 8, 2, rows, interlace=1)
+
+
 def f32(*v):
     return struct.pack("<%df" % len(v), *v)
 
@@ -39,6 +67,10 @@ def write_gltf_assets():
     checker = png_rgb(8, 8, lambda x, y: (255, 200, 40) if (x // 2 + y // 2) % 2 else (20, 60, 220))
     with open(os.path.join(OUT, "checker8.png"), "wb") as f:
         f.write(checker)
+    with open(os.path.join(OUT, "deep16.png"), "wb") as f:
+        f.write(png_rgba16(5, 3))
+    with open(os.path.join(OUT, "adam7.png"), "wb") as f:
+        f.write(png_adam7_rgb(19, 13))
     # ---- multi.bin ----
     blob = bytearray()
     def add(b, align=4):
@@ -113,12 +145,12 @@ def write_gltf_assets():
             {"name": "Painted", "pbrMetallicRoughness": {"baseColorFactor": [0.8, 0.1, 0.3, 0.5], "metallicFactor": 0.25,
                                                           "roughnessFactor": 0.65, "baseColorTexture": {"index": 0},
                                                           "metallicRoughnessTexture": {"index": 1}},
-             "emissiveFactor": [0.1, 0.2, 0.3], "normalTexture": {"index": 1}, "occlusionTexture": {"index": 0},
-             "emissiveTexture": {"index": 1}},
-            {"pbrMetallicRoughness": {"metallicFactor": 1}},
+             "emissiveFactor": [0.1, 0.2, 0.3], "normalTexture": {"index": 1}, "occlusionTexture": {"index": 2},
+             "emissiveTexture": {"index": 3}},
+            {"pbrMetallicRoughness": {"metallicFactor": 1, "baseColorTexture": {"index": 2}}, "normalTexture": {"index": 3}},
         ],
-        "textures": [{"name": "CheckerFromView", "source": 0}, {"source": 1}],
-        "images": [{"bufferView": 9, "mimeType": "image/png"}, {"uri": "checker8.png"}],
+        "textures": [{"name": "CheckerFromView", "source": 0}, {"source": 1}, {"name": "Deep", "source": 2}, {"name": "Interlaced", "source": 3}],
+        "images": [{"bufferView": 9, "mimeType": "image/png"}, {"uri": "checker8.png"}, {"uri": "deep16.png"}, {"uri": "adam7.png"}],
         "extensions": {"KHR_lights_punctual": {"lights": [{"type": "point", "color": [1, 1, 1], "intensity": 5}]}},
         "extensionsUsed": ["KHR_lights_punctual"],
         "accessors": acc, "bufferViews": views, "buffers": [{"uri": "multi.bin", "byteLength": len(blob)}],
