@@ -29,9 +29,13 @@ struct LocalStats {
 // Reciprocal for slab tests: one MUFU.RCP (relative error <= 2^-23) instead of the ~10-instruction IEEE
 // division.  The box test absorbs it: far planes are scaled by kFar = 1 + 2^-20 (see intersect_node).
 __device__ __forceinline__ float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#else // host build of this header (tests/cpu_traverse: the traversal logic checked without a GPU)
+    return 1.0f / x;
+#endif
 }
 __device__ __forceinline__ float safe_rcp(float d) {
     const float ooeps = 8.271806125530277e-25f; // 2^-80
@@ -126,6 +130,7 @@ __device__ __forceinline__ RaySpace make_ray_space(const float3 o, const float3 
 
 // (a0, a1) * b + c and (a0, a1) * b as one packed instruction each; bitwise equal to two fmaf() / __fmul_rn().
 __device__ __forceinline__ float2 fma2_bcast(const float a0, const float a1, const float b, const float c) {
+#ifdef __CUDA_ARCH__
     unsigned long long A, B, C, D;
     float2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
@@ -134,8 +139,12 @@ __device__ __forceinline__ float2 fma2_bcast(const float a0, const float a1, con
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(D));
     return r;
+#else
+    return make_float2(fmaf(a0, b, c), fmaf(a1, b, c));
+#endif
 }
 __device__ __forceinline__ float2 mul2_bcast(const float a0, const float a1, const float b) {
+#ifdef __CUDA_ARCH__
     unsigned long long A, B, D;
     float2 r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
@@ -143,6 +152,9 @@ __device__ __forceinline__ float2 mul2_bcast(const float a0, const float a1, con
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(D));
     return r;
+#else
+    return make_float2(a0 * b, a1 * b);
+#endif
 }
 
 // Returns the 8-bit mask of child slots whose box the ray overlaps in [tmin, tmax].
