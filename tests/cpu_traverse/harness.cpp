@@ -6,7 +6,7 @@
 // PTX sequences have host branches (#ifdef __CUDA_ARCH__).  The wide BVHs are built here by a simple median splitter
 // that emits the same node format as csrc/bvh_build.cu (common.cuh WideNode / WideTri / InstanceRec).
 //
-// usage: harness <seed>   -> one JSON line with agreement counts
+// usage: harness <seed> [instances=40] [rays=6000] [extent=6]   -> one JSON line with agreement counts
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -209,6 +209,8 @@ static bool exhaustive(const std::vector<Mesh>& meshes, const std::vector<Instan
 
 int main(int argc, char** argv) {
     const unsigned seed = argc > 1 ? (unsigned)atoi(argv[1]) : 1u;
+    const int n_inst = argc > 2 ? atoi(argv[2]) : 40, n_rays = argc > 3 ? atoi(argv[3]) : 6000;
+    const double extent = argc > 4 ? atof(argv[4]) : 6.0;
     std::mt19937 rng(seed);
     auto uni = [&](double a, double b) { return std::uniform_real_distribution<double>(a, b)(rng); };
     // meshes: a unit cube, a triangle soup, a displaced grid
@@ -242,7 +244,7 @@ int main(int argc, char** argv) {
     for (auto& m : meshes) prepare(m);
     // instances: random rotation about a random axis, anisotropic scale (one mirrored), translation in a 12^3 box
     std::vector<Instance> inst;
-    for (int i = 0; i < 40; i++) {
+    for (int i = 0; i < n_inst; i++) {
         Instance in;
         in.mesh = i % 3;
         double ax[3] = {uni(-1, 1), uni(-1, 1), uni(-1, 1)};
@@ -255,7 +257,7 @@ int main(int argc, char** argv) {
                              ax[2] * ax[0] * (1 - cs) - ax[1] * sn, ax[2] * ax[1] * (1 - cs) + ax[0] * sn, cs + ax[2] * ax[2] * (1 - cs)};
         for (int r = 0; r < 3; r++) {
             for (int c2 = 0; c2 < 3; c2++) in.m[r * 4 + c2] = R[r * 3 + c2] * sc[c2];
-            in.m[r * 4 + 3] = uni(-6, 6);
+            in.m[r * 4 + 3] = uni(-extent, extent);
         }
         invert(in.m, in.inv);
         inst.push_back(in);
@@ -299,8 +301,9 @@ int main(int argc, char** argv) {
     long hits = 0, rays = 0, agree = 0, clear_rays = 0, clear_agree = 0, hint_same = 0, cand_rays = 0, cand_same = 0, closest_ok = 0, closest_n = 0;
     uint2 stack[LUZ_STACK_SIZE];
     LocalStats st = {0, 0, 0};
-    for (int r = 0; r < 6000; r++) {
-        double o[3] = {uni(-7, 7), uni(-7, 7), uni(-7, 7)}, tgt[3] = {uni(-7, 7), uni(-7, 7), uni(-7, 7)}, d[3];
+    for (int r = 0; r < n_rays; r++) {
+        const double e1 = extent + 1.0;
+        double o[3] = {uni(-e1, e1), uni(-e1, e1), uni(-e1, e1)}, tgt[3] = {uni(-e1, e1), uni(-e1, e1), uni(-e1, e1)}, d[3];
         const bool shortray = r % 3 == 0;
         if (shortray) { // AO-like: start on an instance's surface region, short reach
             const Instance& in = ordered[(size_t)(rng() % ordered.size())];

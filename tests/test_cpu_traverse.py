@@ -37,3 +37,11 @@ def test_host_compiled_traversal_matches_exhaustive(harness, seed):
     assert r["hint_same"] == r["rays"], r                  # an occluder hint never changes the answer
     assert r["cand_rays"] > 1000 and r["cand_same"] == r["cand_rays"], r  # candidate lists == root descent
     assert r["closest_ok"] == r["closest_n"], r            # closest hit: same hit / miss and t within 1e-4
+
+
+def test_host_compiled_traversal_deep_tlas(harness):
+    """600 instances in a denser box: a four-level TLAS, long stacks, most rays occluded."""
+    r = json.loads(subprocess.run([harness, "7", "600", "2500", "9"], stdout=subprocess.PIPE, text=True, check=True).stdout)
+    assert r["rays"] == 2500 and r["tlas_levels"] >= 4 and r["hits"] > 0.3 * r["rays"], r
+    assert r["agree"] >= 0.999 * r["rays"] and r["clear_agree"] == r["clear_rays"], r
+    assert r["hint_same"] == r["rays"] and r["cand_same"] == r["cand_rays"] and r["closest_ok"] == r["closest_n"], r
