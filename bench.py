@@ -77,32 +77,11 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
-def setup_scene(args, rt, host_mod, scenes, tmp):
-    """Loads the workload as a Luz project through the host mirror and uploads its assets."""
-    path, bin_path, cfg = scenes.write_project(args.config, tmp, args.variant)
-    if args.shadow_type != 1 or args.volumetric:
-        # SURVEY 8(f) rank 4 passes on the benchmark scene: shadow-map shadows instead of shadow rays and / or
-        # volumetric lights (not the headline metric; reported in kernels_ms)
-        with open(path) as f:
-            doc = json.load(f)
-        for sc in doc["scenes"].values():
-            sc["shadowType"] = args.shadow_type
-
-            def patch(nodes):
-                for n in nodes:
-                    if n.get("type") == 7:
-                        n["volumetricType"] = args.volumetric
-                        n["shadowMapFar"] = 400.0
-                    patch(n.get("children", []))
-            patch(sc["nodes"])
-        with open(path, "w") as f:
-            json.dump(doc, f)
-    if args.width:
-        cfg["width"], cfg["height"] = args.width, args.height
-    app = host_mod.LuzHost(rt)
-    app.load_project(path, bin_path)
-    app.scene_settings(light_samples=cfg["light_samples"], ao_samples=cfg["ao_samples"])
-    return app, cfg
+def make_workload(args, rt, tmp):
+    """The workload as a Luz project, loaded through the host mirror (luz_b200/workloads.py)."""
+    from luz_b200 import workloads
+    return workloads.Workload(rt, args.config, variant=args.variant, width=args.width, height=args.height,
+                              shadow_type=args.shadow_type, volumetric=args.volumetric, tmp=tmp)
 
 
 def blue_noise(scenes):
@@ -185,11 +164,10 @@ def run_ours(args):
 
     rt = R.LuzRT(device=local, rank=rank, world=world)
     tmp = tempfile.mkdtemp(prefix="luzbench_r%d_" % rank)
-    app, cfg = setup_scene(args, rt, H, scenes, tmp)
-    W, Hh = cfg["width"], cfg["height"]
-    app.set_extent(W, Hh, create_images=True)
-    rt.set_blue_noise(blue_noise(scenes))
-    app.add_assets()
+    wl = make_workload(args, rt, tmp)
+    app, cfg = wl.app, wl.cfg
+    W, Hh = wl.width, wl.height
+    wl.upload(blue_noise(scenes))
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -198,23 +176,9 @@ def run_ours(args):
         rt.comm_init(idt.cpu().numpy())
 
     animate = cfg["animate"]
-    n_nodes = app.mesh_node_count()
-    base = [app.get_mesh_node_transform(i) for i in range(n_nodes)] if animate else None
-    base_pos = np.array([b[0] for b in base], np.float32) if animate else None
-    base_rot = np.array([b[1] for b in base], np.float32) if animate else None
-    tlas_flag = H.FRAME_TLAS_REFIT if animate == "refit" else 0
 
     def step(frame, first=False):
-        if animate:
-            pos, rot = scenes.animate(args.config, frame, n_nodes, base_pos, base_rot)
-            if args.config == "c2":
-                app.set_mesh_node_transforms(1, rot=rot[1:])
-            else:
-                app.set_mesh_node_transforms(0, pos=pos)
-            # moving instances change primary visibility: the G-buffer producer runs too (not part of the metric)
-            app.render_frame(H.FRAME_OPAQUE | (0 if first else tlas_flag))
-        else:
-            app.render_frame(H.FRAME_OPAQUE if first else H.FRAME_NO_UPDATE)
+        wl.step(first)
 
     stream = torch.cuda.ExternalStream(rt.stream(), device=torch.device("cuda", local))
     # frame 0 builds the TLAS, produces the G-buffer on the device (input producer) and seeds the history
@@ -385,6 +349,20 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_baseline_sample(app, rt, R, W, Hh, budget_s=args.cpu_budget)
 
+    # parity of the frames that were just timed: product kernels vs the oracle on a seeded row sample (checker, untimed)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import bench_parity as BP
+        rt.set_debug(0)
+        parity = BP.check_workload(wl, blue_noise(scenes), n_rows=args.parity_rows,
+                                   candidate_rows=strips.owned_rows(rank, world, Hh) if world > 1 else None,
+                                   taa=(world == 1))
+        parity["pass"] = bool(parity["agree"] >= BP.MASK_AGREE and parity["max_abs_mask_identical_pixels"] <= BP.RADIANCE_TOL
+                              and (parity["max_abs"] <= BP.RADIANCE_TOL or parity["psnr_db"] >= 50.0)
+                              and parity.get("taa_max_abs", 0.0) <= BP.TAA_TOL
+                              and parity.get("bvh2_check", {"rays_differ": 0})["rays_differ"] == 0)
+
     if rank == 0:
         hbm_peak, hbm_src = read_peaks()
         l2_gbs = rt.probe_read_bandwidth(32 << 20, 200)
@@ -395,14 +373,24 @@ def run_ours(args):
         nodes, tris, insts, rays_r = float(sm[7]) / world, float(sm[8]) / world, float(sm[9]) / world, rays_frame / world
         trav_bytes = 80.0 * nodes + 48.0 * tris + 64.0 * insts
         shade_rows = len(strips.shaded_rows(rank, world, Hh))
-        light_bytes = trav_bytes + 48.0 * W * shade_rows
+        rays_ms = max(kavg["light_rays_ms"], 1e-6)
+        shade_ms = max(kavg["light_ms"] - kavg["light_rays_ms"], 1e-6)
+        # The ray kernel's bound: the BVH of every instanced configuration (a few MB) is cache resident, so the memory
+        # roofline that applies to traversal is the L2 read bandwidth ("vs measured L2 or HBM peak as
+        # applicable"), probed in this run; the unique-BLAS variant (~2 GB of BVH) streams from HBM.
+        unique = args.variant == "unique"
+        trav_peak = hbm_peak if unique else l2_gbs
+        words = max((app.light_count() * cfg["light_samples"] + 31) // 32, 1) + max((cfg["ao_samples"] + 31) // 32, 1)
+        rays_stream = (20.0 + 4.0 * words) * W * shade_rows     # normal 16 + depth 4 in, mask words out
+        shade_stream = (48.0 + 4.0 * words) * W * shade_rows    # G-buffer 32 in, masks in, radiance 16 out
+        src_hash = kernel_source_hash()
         out = {
             "metric": METRIC, "value": rays_frame / ms_per_step / 1e3, "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px%s" % (
-                args.config, W, Hh, len(app.instances()), app.light_count(), cfg["light_samples"], cfg["ao_samples"],
-                (", TLAS %s per frame" % animate) if animate else "") +
+            "config": {"workload": "%s%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px%s" % (
+                args.config, "-unique" if unique else "", W, Hh, len(app.instances()), app.light_count(),
+                cfg["light_samples"], cfg["ao_samples"], (", TLAS %s per frame" % animate) if animate else "") +
                 (", shadowType 2 (shadow maps, %d^2)" % 1024 if args.shadow_type == 2 else "") +
                 (", volumetricType %d on every light" % args.volumetric if args.volumetric else ""),
                 "parallelism": ("round-robin bands of %d rows x%d + ncclAllGather" % (strips.band_rows(Hh, world), world))
@@ -418,32 +406,38 @@ def run_ours(args):
                            "shadow_map": kavg["shadow_map_ms"] if (args.shadow_type == 2 or args.volumetric == 2) else 0.0},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            # the dominant kernel against the measured HBM copy peak (the contract's roofline); its BVH working set is
-            # L1/L2 resident, so the same algorithmic bytes are also shown against the L2 read bandwidth probed in
-            # this run (roofline_l2).  traffic = ncu dram bytes per launch of the committed profile, when it is for
-            # this workload.
-            "roofline": {"kernel": "light pass = k_shadow_hints + k_light_rays_split (ray generation + any-hit traversal, the dominant "
-                                   "kernel) + k_light_shade (Cook-Torrance), timed together", "bound": "hbm",
-                         "achieved": light_bytes / (light_ms * 1e6), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": light_bytes / (light_ms * 1e6) / hbm_peak, "traffic": ncu_traffic(args, "light_pass"),
-                         "peak_source": hbm_src,
-                         "algorithmic_bytes": "SURVEY 8(d): 48 B/px streamed (32 B G-buffer + 16 B radiance) + per ray 80 B/node "
-                                              "+ 48 B/triangle + 64 B/instance (the 80 B is the contract's figure for a "
-                                              "compressed node; this build fetches 208-B fp32 nodes)",
-                         "stream_bytes": 48.0 * W * shade_rows, "traversal_bytes": trav_bytes,
+            # the dominant kernel (ray generation + any-hit traversal) against the memory level its working set lives in
+            "roofline": {"kernel": "k_shadow_hints + ray kernel (k_light_rays_*: ray generation + any-hit traversal, the dominant "
+                                   "kernel), timed with CUDA events on the launch stream", "bound": "hbm" if unique else "l2",
+                         "achieved": (trav_bytes + rays_stream) / (rays_ms * 1e6), "peak": trav_peak, "unit": "GB/s",
+                         "frac": (trav_bytes + rays_stream) / (rays_ms * 1e6) / trav_peak if trav_peak else None,
+                         "traffic": ncu_traffic(args, "light_rays", src_hash),
+                         "peak_source": hbm_src if unique else "luzrt_probe_read_bandwidth, 32 MiB L2-resident buffer, measured in this run",
+                         "algorithmic_bytes": "SURVEY 8(d): per ray 80 B/node + 48 B/triangle + 64 B/instance (counted by the "
+                                              "statistics variant of the same kernel on the same BVH and rays) + 20 B/px "
+                                              "normal+depth in + 4 B/px per mask word out",
+                         "stream_bytes": rays_stream, "traversal_bytes": trav_bytes, "ms": rays_ms,
                          "bytes_per_ray": trav_bytes / max(rays_r, 1.0),
                          "nodes_per_ray": nodes / max(rays_r, 1.0),
                          "tris_per_ray": tris / max(rays_r, 1.0),
                          "instances_per_ray": insts / max(rays_r, 1.0),
                          "occluded_fraction": float(st.rays_occluded) / max(float(st.rays), 1.0),
-                         "grays_per_s_per_gpu": rays_r / (light_ms * 1e6)},
-            "roofline_l2": {"kernel": "light pass (k_shadow_hints + k_light_rays_split + k_light_shade)", "bound": "l2", "achieved": light_bytes / (light_ms * 1e6),
-                            "peak": l2_gbs, "unit": "GB/s", "frac": light_bytes / (light_ms * 1e6) / l2_gbs if l2_gbs else None,
-                            "peak_source": "luzrt_probe_read_bandwidth, 32 MiB resident buffer, measured in this run"},
+                         "grays_per_s_per_gpu": rays_r / (rays_ms * 1e6),
+                         "hbm_equivalent_frac": (trav_bytes + rays_stream) / (rays_ms * 1e6) / hbm_peak,
+                         "note": "rays of pixels whose AO candidate list is empty are resolved by the per-pixel TLAS box query "
+                                 "and count as traced (they are any-hit rays of the frame, answered exactly)"},
+            "roofline_shade": {"kernel": "k_light_shade", "bound": "hbm", "achieved": shade_stream / (shade_ms * 1e6),
+                               "peak": hbm_peak, "unit": "GB/s", "frac": shade_stream / (shade_ms * 1e6) / hbm_peak,
+                               "traffic": ncu_traffic(args, "k_light_shade", src_hash), "peak_source": hbm_src, "ms": shade_ms,
+                               "algorithmic_bytes": "48 B/px (32 B G-buffer + 16 B radiance) + 4 B/px per mask word"},
             "roofline_taa": {"kernel": "k_taa", "bound": "hbm", "achieved": 52.0 * own_px / (taa_ms * 1e6),
                              "peak": hbm_peak, "unit": "GB/s", "frac": 52.0 * own_px / (taa_ms * 1e6) / hbm_peak,
-                             "traffic": ncu_traffic(args, "k_taa"), "peak_source": hbm_src, "hbm_read_probe_gbs": hbm_probe},
+                             "traffic": ncu_traffic(args, "k_taa", src_hash), "peak_source": hbm_src, "hbm_read_probe_gbs": hbm_probe,
+                             "ms": taa_ms},
+            "l2_read_probe_gbs": l2_gbs,
         }
+        if parity:
+            out["parity"] = parity
         if e2e:
             out["e2e"] = {"value": rays_frame / float(mx[2]) / 1e3, "unit": "Mrays/s", "ms_per_step": float(mx[2]),
                           "mode": "host G-buffer in, resolved rows out every step; copies of successive steps overlapped "
@@ -461,14 +455,27 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic(args, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/
-    traffic.json, written from the .ncu-rep by profiles/summarize.py), if one exists for this workload."""
+def kernel_source_hash():
+    """sha1 over the CUDA sources: ties an ncu capture (profiles/traffic.json) to the code it was taken from."""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "luz_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            with open(os.path.join(d, f), "rb") as fh:
+                h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(args, kernel, src_hash):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture
+    (profiles/traffic.json, written from the .ncu-rep by profiles/summarize.py).  The capture carries the hash of the
+    kernel sources it was taken from: a capture of other code is stale and reported as null."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         key = args.config + ("-" + args.variant if args.variant else "")
-        if args.width or args.gpus != 1:
+        if args.width or args.gpus != 1 or t.get("source_hash") != src_hash:
             return None
         return t.get(key, {}).get(kernel)
     except Exception:
@@ -496,12 +503,15 @@ def cpu_baseline_sample(app, rt, R, W, Hh, budget_s=15.0):
 def time_oracle_rows(O, world, sb, extra, gb, W, Hh, budget_s, kind):
     from luz_b200 import scenes
     bn = blue_noise(scenes)
+    O.lib().orc_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    cores = O.lib().orc_get_threads()
     mid = Hh // 2
+    probe = min(cores, Hh)  # one row per thread (rows are the unit of the oracle's OpenMP loop)
     t0 = time.perf_counter()
-    rc, _, _, _, st = O.light_pass(sb, gb, 0, bn, world, extra_lights=extra, exhaustive=False, rows=(mid, mid + 2))
+    rc, _, _, _, st = O.light_pass(sb, gb, 0, bn, world, extra_lights=extra, exhaustive=False, rows=(mid, mid + probe))
     dt = max(time.perf_counter() - t0, 1e-4)
-    rows = int(max(2, min(Hh, 2 * budget_s / dt)))
-    y0 = max(0, mid - rows // 2)
+    rows = int(max(min(4 * cores, Hh), min(Hh, probe * budget_s / dt)))
+    y0 = max(0, min(Hh - rows, mid - rows // 2))
     t0 = time.perf_counter()
     rc, _, _, _, st = O.light_pass(sb, gb, 0, bn, world, extra_lights=extra, exhaustive=False, rows=(y0, y0 + rows))
     dt = time.perf_counter() - t0
@@ -516,20 +526,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from luz_b200 import host as H
     from luz_b200 import scenes
     tmp = tempfile.mkdtemp(prefix="luzbench_ref_")
-    app, cfg = setup_scene(args, None, H, scenes, tmp)
-    W, Hh = cfg["width"], cfg["height"]
-    app.set_extent(W, Hh, create_images=False)
-    app.add_assets()
+    wl = make_workload(args, None, tmp)
+    app, cfg = wl.app, wl.cfg
+    W, Hh = wl.width, wl.height
+    wl.upload(None)
     app.update_resources()
     O, world = oracle_world(app)
+    # all host cores, whatever OMP_NUM_THREADS the launcher exported (torchrun sets it to 1)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.lib().orc_set_threads(cores)
     sb, extra = app.scene_block(), app.extra_lights()
     models, n_models = app.models()
-    # bounded sample: a band of rows in the middle of the frame; its G-buffer is produced by the oracle's
-    # own generator (input, untimed)
-    rows = max(2, args.ref_rows)
+    # bounded sample: a band of rows in the middle of the frame, at least 4 rows per core so that every core works
+    # (rows are the unit of the oracle's OpenMP loop); its G-buffer is produced by the oracle's own generator (untimed)
+    rows = min(Hh - 2, max(args.ref_rows if args.ref_rows else 4 * cores, 64 if not args.ref_rows else 2))
     y0 = Hh // 2 - rows // 2
     gb = O.gbuffer_pass(sb, world, models, n_models, app.textures(), W, Hh, exhaustive=False, rows=(y0, y0 + rows))
     bn = blue_noise(scenes)
@@ -544,18 +556,19 @@ def run_reference(args):
             rays = st.rays
     ms = float(np.mean(times)) * 1e3
     val = rays / (ms * 1e3)
-    cores = O.lib().orc_get_threads()
-    sample = ("rows [%d,%d) of the %dx%d frame per step (%d rays); CPU restatement of light.frag/taa.comp with a BVH2 "
-              "traverser, not the Vulkan/lavapipe path (no Vulkan loader, glslang or lavapipe in the image)" % (
-                  y0, y0 + rows, W, Hh, rays))
+    threads = O.lib().orc_get_threads()
+    sample = ("rows [%d,%d) of the %dx%d frame per step (%d rays, %d threads); CPU restatement of light.frag/taa.comp with a "
+              "BVH2 traverser, not the Vulkan/lavapipe path (no Vulkan loader, glslang or lavapipe in the image)" % (
+                  y0, y0 + rows, W, Hh, rays, threads))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px" % (
-            args.config, W, Hh, len(app.instances()), app.light_count(), cfg["light_samples"], cfg["ao_samples"]),
+        "config": {"workload": "%s%s: %dx%d, %d instances, %d lights x %d shadow + %d AO rays/px%s" % (
+            args.config, "-unique" if args.variant == "unique" else "", W, Hh, len(app.instances()), app.light_count(),
+            cfg["light_samples"], cfg["ao_samples"], (", TLAS %s per frame" % cfg["animate"]) if cfg["animate"] else ""),
             "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
@@ -579,7 +592,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--ref-rows", type=int, default=16)
+    ap.add_argument("--ref-rows", type=int, default=0, help="rows per step of the CPU arm (0: 4 x host cores, >= 64)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity-rows", type=int, default=64)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -19,7 +19,8 @@
  *  - calls are asynchronous and ordered on the ctx's CUDA stream, except luzrt_read,
  *    luzrt_sync, luzrt_blas_create (blocking like GPUScene::AddMesh's WaitQueue,
  *    GPUScene.cpp:132-137) and luzrt_create/destroy.
- *  - one host thread per ctx (the reference is single threaded); no global state.
+ *  - one host thread per ctx (the reference is single threaded).  The only process-global state is the
+ *    lazily dlopen'ed NCCL library handle shared by every ctx (loaded on the first luzrt_comm_* call).
  *  - there is no CPU fallback: if no sm_100-class CUDA device is usable luzrt_create fails.
  *
  * Images are row-major, row 0 = top (Vulkan viewport, VulkanWrapper.cpp:1216-1222).
@@ -91,8 +92,9 @@ enum {
 typedef struct luzrt_stats {
     uint64_t lit_pixels;        /* pixels with length(N) != 0                         */
     uint64_t rays;              /* shadow + AO any-hit rays actually traced           */
-    uint64_t nodes_visited;     /* 80-B wide nodes fetched (TLAS + BLAS)              */
-    uint64_t triangles_tested;  /* 48-B triangles fetched                             */
+    uint64_t nodes_visited;     /* 8-wide nodes fetched, TLAS + BLAS (this build: 208-B fp32 nodes; the
+                                   roofline's algorithmic figure is SURVEY 8(d)'s 80 B)              */
+    uint64_t triangles_tested;  /* triangles fetched (this build: 96-B Pluecker records; SURVEY 8(d): 48 B) */
     uint64_t instances_entered; /* 64-B instance records fetched                      */
     uint64_t rays_occluded;
 } luzrt_stats;
@@ -112,8 +114,11 @@ typedef struct luzrt_timings {
 /* ---- lifetime ------------------------------------------------------------------------- */
 
 /* Replaces vkw::Init + DeferredRenderer::CreateResources for this path.  One ctx drives one
- * GPU.  For an image-partitioned multi-GPU frame create one ctx per process/GPU with its
- * rank in [0, world); rank r owns rows [r*H/world, (r+1)*H/world).  world = 1 for a single GPU. */
+ * GPU.  For an image-partitioned multi-GPU frame create one ctx per GPU with its rank in [0, world)
+ * (one process per GPU, or all of them in one process through luzrt_create_multi).  The frame is cut
+ * into bands of rows that are dealt ROUND-ROBIN (band b belongs to rank b % world, see luzrt_owned_bands):
+ * a rank does NOT own one contiguous strip.  Hosts place luzrt_read_owned / luzrt_device_ptr data with
+ * luzrt_owned_bands, never by assuming [r*H/world, (r+1)*H/world).  world = 1 for a single GPU. */
 LUZRT_API int luzrt_create(int device_id, int rank, int world, luzrt_ctx** out);
 LUZRT_API void luzrt_destroy(luzrt_ctx* ctx);
 LUZRT_API const char* luzrt_last_error(luzrt_ctx* ctx);

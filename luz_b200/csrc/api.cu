@@ -596,6 +596,15 @@ int luzrt_blas_destroy(luzrt_ctx* c, luzrt_blas h) {
     CU(c, cudaStreamSynchronize(c->stream));
     free_blas(c->blas[h]);
     c->blas_attr_dirty = true;
+    // the current TLAS's instance records hold raw device pointers into the BLAS that was just freed: passes must not
+    // traverse it, and a later "refit" against a BLAS that reuses the slot must be a rebuild
+    for (luzrt_blas used : c->last_blas)
+        if (used == h) {
+            c->have_tlas = false;
+            c->shadow_maps_current = false;
+            c->last_blas.clear();
+            break;
+        }
     return LUZRT_OK;
 }
 
@@ -696,9 +705,12 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     c->shadow_maps_current = false; // the maps were rendered from the previous TLAS
     c->last_blas.resize(count);
     for (uint32_t i = 0; i < count; i++) c->last_blas[i] = instances[i].blas;
-    if (c->tlas.levels.size() + max_blas_levels + 3 > LUZ_STACK_SIZE)
+    if (c->tlas.levels.size() + max_blas_levels + 3 > LUZ_STACK_SIZE) {
+        c->have_tlas = false; // no pass may traverse it: the stack would overflow
+        c->last_blas.clear();
         return fail(c, LUZRT_E_INVALID, "BVH too deep for the traversal stack (%zu + %u levels)", c->tlas.levels.size(),
                     max_blas_levels);
+    }
     return LUZRT_OK;
 }
 
@@ -914,6 +926,10 @@ int luzrt_read_wait(luzrt_ctx* c) {
     return LUZRT_OK;
 }
 
+namespace {
+double det3_rows(const float* m, int r0, int r1, int r2);
+}
+
 int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_models) {
     if (!c) return LUZRT_E_INVALID;
     if (!c->w) return fail(c, LUZRT_E_STATE, "luzrt_resize has not been called");
@@ -973,6 +989,17 @@ int luzrt_gbuffer_pass(luzrt_ctx* c, const luzw_model_block* models, uint32_t n_
     a.material = c->material;
     a.emission = c->emission;
     a.depth = c->depth;
+    { // the Opaque Pipeline culls back faces (front = counter-clockwise in the framebuffer; DeferredRenderer.cpp
+      // "Opaque Pipeline" leaves cullFront false, VulkanWrapper.cpp:941-946): with the sign s_view of the view's linear
+      // part (rows x, y, w of a perspective viewProj; x, y, z of an orthographic one) a triangle is front-facing iff
+      // s_view * sign(det M_instance) * dot(d, (v1 - v0) x (v2 - v0)) < 0 along the primary ray d (shadow_map.cu has
+      // the derivation); trace_ray<FACE_CULL> keeps the triangles with cull_sign * sign(det M) * dot(d, n) > 0
+        const float* m = c->fc.view_proj;
+        const bool ortho = m[3] == 0.0f && m[7] == 0.0f && m[11] == 0.0f;
+        const double d = det3_rows(m, 0, 1, ortho ? 2 : 3);
+        if (d == 0.0 || d != d) return fail(c, LUZRT_E_INVALID, "scene.viewProj is singular");
+        a.cull_sign = d < 0.0 ? 1.0f : -1.0f;
+    }
     // screen-space volumetrics read depth anywhere in the frame: every rank then renders all rows
     a.rows = (c->need_full_depth && c->world > 1) ? BandSet{0, c->h, c->h, 1} : shade_bands(c);
     ev_begin(c, EV_GBUF);

@@ -5,8 +5,12 @@
 // DeferredRenderer.cpp:176-238, clears colour 0 / depth 1 VulkanWrapper.cpp:1194-1196, :1212).
 // Here the same five attachments come from the closest hit of the primary ray through each pixel
 // centre, traced through the same TLAS/BLAS as the shadow rays; the fragment-stage arithmetic
-// (material fetches, alpha test, TBN normal) follows opaque.frag.  Coverage differs from the
-// rasteriser only on triangle edges.
+// (material fetches, alpha test, TBN normal) follows opaque.frag.  The Opaque Pipeline culls back
+// faces (VK_CULL_MODE_BACK_BIT, front = counter-clockwise; VulkanWrapper.cpp:941-946): the primary ray
+// ignores back-facing triangles the same way (trace_ray<FACE_CULL>, sign from the camera's viewProj and
+// the instance determinant), so a camera inside a mesh, single-sided planes seen from behind and
+// mirrored instances give the reference's coverage.  What remains different from the rasteriser is
+// coverage on triangle edges.
 #include "passes.h"
 #include "traverse.cuh"
 
@@ -72,7 +76,8 @@ __global__ void __launch_bounds__(128) k_gbuffer(const GbufferArgs a) {
     float3 N = f3(0, 0, 0);
     for (int iter = 0; iter < 16 && !have; iter++) {
         HitInfo h;
-        if (!trace_ray<true, false>(a.scene, pn, d, tmin, 1.0f, &h, nullptr, stack)) break;
+        h.cull_sign = a.cull_sign;
+        if (!trace_ray<true, false, true>(a.scene, pn, d, tmin, 1.0f, &h, nullptr, stack)) break;
         const InstanceMeta im = a.inst_meta[h.inst];
         if (im.custom_index >= a.n_models) break;
         const luzw_model_block& mb = a.models[im.custom_index];

@@ -338,11 +338,6 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
     }
     if (lit) bits.flush();
 
-    // ---- counters: lit pixels always (the ray count of the frame follows from it) ----
-    const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted && PART <= 0));
-    if (lane == 0 && lit_warp)
-        atomicAdd(a.lit_counters + 16 * ((blockIdx.x * 4u + (blockIdx.y + blockIdx.z * 7u) * 29u + warp) & 63u),
-                  (unsigned long long)lit_warp);
     if (STATS) {
         unsigned long long vals[5] = {n_rays, st.nodes, st.tris, st.insts, n_occl};
 #pragma unroll
@@ -414,6 +409,14 @@ __global__ void __launch_bounds__(128) k_light_shade(const LightArgs a) {
     const float3 ambientLight = f3(fc.ambient[0], fc.ambient[1], fc.ambient[2]);
     const bool lit = in_image && (length3(N) != 0.0f); // :178
     if (in_image && !lit) a.out[opix] = make_float4(ambientLight.x, ambientLight.y, ambientLight.z, 1.0f);
+    { // lit pixels of the rows this rank owns (halo rows are recomputation): the frame's ray count follows from it,
+      // whichever ray kernels ran (shadow rays only, AO rays only, both, none)
+        const bool counted = r >= a.count_row_begin && r < a.count_row_end;
+        const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted));
+        if (lane == 0 && lit_warp)
+            atomicAdd(a.lit_counters + 16 * ((blockIdx.x + (blockIdx.y * 4u + warp + blockIdx.z * 7u) * 29u) & 63u),
+                      (unsigned long long)lit_warp);
+    }
 
     const float3 albedo = f3(powf((float)a8.x / 255.0f, 2.2f), powf((float)a8.y / 255.0f, 2.2f),
                              powf((float)a8.z / 255.0f, 2.2f));

@@ -58,6 +58,7 @@ struct GbufferArgs {
     uchar4* emission;
     float* depth;
     BandSet rows;
+    float cull_sign; // -s_view of the camera: back faces are culled (api.cu luzrt_gbuffer_pass)
 };
 
 // one light with a volumetric type (LightBlock fields the volumetric shaders read), scene order

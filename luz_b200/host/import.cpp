@@ -148,14 +148,28 @@ bool resolve(const GltfModel& m, int64_t accessor_index, View& out, std::string&
     const int64_t buffer = int_or(*bv, "buffer", -1);
     if (buffer < 0 || (size_t)buffer >= m.buffers.size()) { err = "bufferView.buffer out of range"; return false; }
     const std::vector<uint8_t>& b = m.buffers[(size_t)buffer];
-    const uint64_t off = (uint64_t)int_or(*bv, "byteOffset", 0) + (uint64_t)int_or(*acc, "byteOffset", 0);
+    // every quantity is validated as a signed 64-bit value before it is cast: negative offsets / strides / counts in a
+    // crafted file must not wrap into range
+    const int64_t view_off = int_or(*bv, "byteOffset", 0), acc_off = int_or(*acc, "byteOffset", 0);
+    const int64_t count = int_or(*acc, "count", 0);
+    if (view_off < 0 || acc_off < 0 || (uint64_t)view_off > b.size() || (uint64_t)acc_off > b.size()) {
+        err = "accessor starts outside its buffer";
+        return false;
+    }
+    if (count < 0 || count > (int64_t)UINT32_MAX) { err = "bad accessor count"; return false; }
+    const uint64_t off = (uint64_t)view_off + (uint64_t)acc_off;
     out.component_type = (int)int_or(*acc, "componentType", 0);
     const int csize = component_size(out.component_type), ncomp = type_components(str_or(*acc, "type", ""));
     if (!csize || !ncomp) { err = "bad accessor type"; return false; }
     const int64_t view_stride = int_or(*bv, "byteStride", 0);
+    // glTF 2.0: byteStride, when present, lies in [4, 252] and holds at least one element
+    if (view_stride && (view_stride < (int64_t)csize * ncomp || view_stride > 252)) {
+        err = "byteStride out of range";
+        return false;
+    }
     out.stride_bytes = view_stride ? (int)view_stride : csize * ncomp;
     if (view_stride && view_stride % csize) { err = "byteStride is not a multiple of the component size"; return false; }
-    out.count = (uint32_t)int_or(*acc, "count", 0);
+    out.count = (uint32_t)count;
     if (off > b.size()) { err = "accessor starts outside its buffer"; return false; }
     out.data = b.data() + off;
     out.available = b.size() - off;

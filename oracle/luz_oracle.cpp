@@ -329,8 +329,31 @@ struct Hit {
     float bu, bv;
 };
 
+// Back-face culling of a rasterising pipeline (the Opaque Pipeline: VK_CULL_MODE_BACK_BIT, front = counter-clockwise in
+// framebuffer space, DeferredRenderer.cpp "Opaque Pipeline" / VulkanWrapper.cpp:941-946), decided the way the
+// rasteriser decides it: from the clip coordinates c_i = viewProj * model * p_i of the triangle's vertices.  The signed
+// framebuffer area has the sign of -det[c_0; c_1; c_2] over (x, y, w); the triangle is front-facing iff the determinant
+// is negative (see the shadow-map pass below, which culls the other side).
+struct FaceCull {
+    const float* view_proj; // column-major mat4, or nullptr: two-sided
+    const float* model;     // the instance's model matrix
+};
+inline bool front_facing(const FaceCull& fc, const float* p0, const float* p1, const float* p2) {
+    double c[3][3];
+    const float* ps[3] = {p0, p1, p2};
+    for (int k = 0; k < 3; k++) {
+        const V4 wv = mul(fc.model, V4{ps[k][0], ps[k][1], ps[k][2], 1.0f});
+        const V4 cv = mul(fc.view_proj, wv);
+        c[k][0] = cv.x, c[k][1] = cv.y, c[k][2] = cv.w;
+    }
+    const double D = c[0][0] * (c[1][1] * c[2][2] - c[1][2] * c[2][1]) - c[0][1] * (c[1][0] * c[2][2] - c[1][2] * c[2][0]) +
+                     c[0][2] * (c[1][0] * c[2][1] - c[1][1] * c[2][0]);
+    return D < 0.0;
+}
+
 // mesh-level search in object space; closest == false returns at the first accepted hit
-bool mesh_trace(const MeshData& md, V3 o, V3 d, float tmin, float& tmax, bool closest, bool exhaustive, Hit& hit) {
+bool mesh_trace(const MeshData& md, V3 o, V3 d, float tmin, float& tmax, bool closest, int exhaustive, Hit& hit,
+                const FaceCull* cull = nullptr) {
     if (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f) return false;
     const RayPre r = make_ray(o, d);
     bool found = false;
@@ -341,6 +364,7 @@ bool mesh_trace(const MeshData& md, V3 o, V3 d, float tmin, float& tmax, bool cl
         const float* p2 = &md.pos[3 * (size_t)md.idx[3 * p + 2]];
         float t, bu, bv;
         if (tri_hit(r, p0, p1, p2, tmin, tmax, &t, &bu, &bv)) {
+            if (cull && !front_facing(*cull, p0, p1, p2)) return false; // culled triangles produce no fragment
             tmax = t;
             hit.t = t;
             hit.prim = (int32_t)p;
@@ -374,7 +398,11 @@ bool mesh_trace(const MeshData& md, V3 o, V3 d, float tmin, float& tmax, bool cl
     return found;
 }
 
-bool world_trace(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool closest, bool exhaustive, Hit& hit) {
+// exhaustive: 0 = BVH2 traversal; 1 = every triangle of every instance (truth, O(rays * triangles)); 2 = every instance
+// whose world box the ray segment meets (no hierarchy), every triangle inside it -- the check of the BVH2 topology for
+// scenes of 10 M instanced triangles, where mode 1 is out of reach
+bool world_trace(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool closest, int exhaustive, Hit& hit,
+                 const float* cull_view_proj = nullptr) {
     hit.t = std::numeric_limits<float>::infinity();
     hit.inst = -1;
     hit.prim = -1;
@@ -387,7 +415,8 @@ bool world_trace(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool cl
         const V3 od = xform_dir(in.inv, d);
         if (ray_is_nan(oo, od)) return false;
         Hit h = hit;
-        if (mesh_trace(w->meshes[in.mesh], oo, od, tmin, tmax, closest, exhaustive, h)) {
+        const FaceCull fcull{cull_view_proj, in.m};
+        if (mesh_trace(w->meshes[in.mesh], oo, od, tmin, tmax, closest, exhaustive, h, cull_view_proj ? &fcull : nullptr)) {
             hit = h;
             hit.inst = (int32_t)ii;
             found = true;
@@ -395,13 +424,15 @@ bool world_trace(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool cl
         }
         return false;
     };
+    const V3 id = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     if (exhaustive) {
-        for (uint32_t ii = 0; ii < w->inst.size(); ii++)
+        for (uint32_t ii = 0; ii < w->inst.size(); ii++) {
+            if (exhaustive == 2 && !box_hit(w->inst[ii].world_box, o, id, tmin, tmax)) continue;
             if (visit(ii) && !closest) return true;
+        }
         return found;
     }
     if (w->inst.empty()) return false;
-    const V3 id = {1.0f / d.x, 1.0f / d.y, 1.0f / d.z};
     uint32_t stack[64];
     int sp = 0;
     stack[sp++] = 0;
@@ -419,7 +450,7 @@ bool world_trace(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool cl
     return found;
 }
 
-inline bool occluded(const orc_world* w, V3 o, V3 d, float tmin, float tmax, bool exhaustive) {
+inline bool occluded(const orc_world* w, V3 o, V3 d, float tmin, float tmax, int exhaustive) {
     Hit h;
     return world_trace(w, o, d, tmin, tmax, false, exhaustive, h);
 }
@@ -541,7 +572,7 @@ V3 fresnel_schlick(float cosTheta, V3 F0) {
 struct PixelCtx {
     const luzw_scene_block* scene;
     const orc_world* world;
-    bool exhaustive;
+    int exhaustive;
     float bn_r, bn_g; // blue-noise texel .rg for this pixel, already /255
     int frame_mod;    // frame % 128
     uint64_t rays, occl;
@@ -696,7 +727,7 @@ void orc_trace_any(const orc_world* w, uint32_t n, const float* o, const float* 
 #pragma omp parallel for schedule(dynamic, 256) ORC_NT
     for (int64_t i = 0; i < (int64_t)n; i++)
         hit[i] = occluded(w, v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]),
-                          tmin[i], tmax[i], exhaustive != 0)
+                          tmin[i], tmax[i], exhaustive)
                      ? 1
                      : 0;
 }
@@ -707,7 +738,7 @@ void orc_trace_closest(const orc_world* w, uint32_t n, const float* o, const flo
     for (int64_t i = 0; i < (int64_t)n; i++) {
         Hit h;
         world_trace(w, v3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), v3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), tmin[i],
-                    tmax[i], true, exhaustive != 0, h);
+                    tmax[i], true, exhaustive, h);
         t[i] = h.t;
         inst[i] = h.inst;
         prim[i] = h.prim;
@@ -748,6 +779,24 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
                    const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
                    int exhaustive, uint32_t y0, uint32_t y1, float* out, uint32_t* shadow_mask,
                    uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words, orc_stats* stats) {
+    if (y1 < y0) return -2;
+    std::vector<uint32_t> rows(y1 - y0);
+    for (uint32_t y = y0; y < y1; y++) rows[y - y0] = y;
+    return orc_light_pass_rows(scene, extra_lights, n_extra, width, height, gb, frame, blue_noise_rgba8, bn_w, bn_h, world,
+                               exhaustive, rows.data(), (uint32_t)rows.size(), 0u, width, out, shadow_mask, shadow_words,
+                               ao_mask, ao_words, stats);
+}
+
+// The same over an arbitrary list of rows (benchmark-scale parity checks sample rows of a 4K / 8K frame).
+int orc_light_pass_rows(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                        uint32_t width, uint32_t height, const orc_gbuffer* gb, uint32_t frame,
+                        const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
+                        int exhaustive, const uint32_t* row_list, uint32_t n_rows, uint32_t x0, uint32_t x1, float* out,
+                        uint32_t* shadow_mask, uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words,
+                        orc_stats* stats) {
+    if (x1 > width || x0 > x1) return -2;
+    for (uint32_t k = 0; k < n_rows; k++)
+        if (row_list[k] >= height) return -2;
     const int numLights = scene->num_lights + (int)n_extra;
     if (scene->shadow_type == LUZW_SHADOW_MAP) { // the maps come from orc_bind_shadow_maps
         for (int i = 0; i < numLights; i++)
@@ -758,9 +807,9 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
     uint64_t tot_rays = 0, tot_occl = 0, tot_lit = 0;
     int frame_signed = (int)frame;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_rays, tot_occl, tot_lit) ORC_NT
-    for (int64_t yy = (int64_t)y0; yy < (int64_t)y1; yy++) {
-        const uint32_t y = (uint32_t)yy;
-        for (uint32_t x = 0; x < width; x++) {
+    for (int64_t yy = 0; yy < (int64_t)n_rows; yy++) {
+        const uint32_t y = row_list[yy];
+        for (uint32_t x = x0; x < x1; x++) {
             const size_t pix = (size_t)y * width + x;
             float* o = out + 4 * pix;
             uint32_t* smask = shadow_mask ? shadow_mask + pix * shadow_words : nullptr;
@@ -802,7 +851,7 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
             PixelCtx c{};
             c.scene = scene;
             c.world = world;
-            c.exhaustive = exhaustive != 0;
+            c.exhaustive = exhaustive;
             c.frame_mod = frame_signed % 128;
             {
                 const int bx = (int)modf_glsl((float)x + 0.5f, (float)bn_w);
@@ -1404,7 +1453,8 @@ int orc_gbuffer_pass(const luzw_scene_block* scene, const orc_world* world, cons
             V3 N{};
             float depth = 1.0f;
             for (int iter = 0; iter < 16 && !have; iter++) {
-                if (!world_trace(world, pn, d, tmin, 1.0f, true, exhaustive != 0, h)) break;
+                // the Opaque Pipeline culls back faces: only front-facing triangles produce fragments
+                if (!world_trace(world, pn, d, tmin, 1.0f, true, exhaustive, h, scene->view_proj)) break;
                 const InstData& in = world->inst[h.inst];
                 const MeshData& md = world->meshes[in.mesh];
                 if (in.custom_index >= n_models) {

@@ -81,6 +81,15 @@ int orc_light_pass(const luzw_scene_block* scene, const luzw_light_block* extra_
                    const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
                    int exhaustive, uint32_t y0, uint32_t y1, float* out_rgba32f, uint32_t* shadow_mask,
                    uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words, orc_stats* stats);
+/* The same over columns [x0, x1) of the n_rows rows listed in row_list (any order, each < height).
+ * exhaustive: 0 BVH2; 1 every triangle of every instance; 2 every instance whose world box the ray segment meets,
+ * every triangle inside (no hierarchy; what validates the BVH2 on 10 M-triangle scenes). */
+int orc_light_pass_rows(const luzw_scene_block* scene, const luzw_light_block* extra_lights, uint32_t n_extra,
+                        uint32_t width, uint32_t height, const orc_gbuffer* gb, uint32_t frame,
+                        const uint8_t* blue_noise_rgba8, uint32_t bn_w, uint32_t bn_h, const orc_world* world,
+                        int exhaustive, const uint32_t* row_list, uint32_t n_rows, uint32_t x0, uint32_t x1,
+                        float* out_rgba32f, uint32_t* shadow_mask, uint32_t shadow_words, uint32_t* ao_mask, uint32_t ao_words,
+                        orc_stats* stats);
 
 /* taa.comp main() over rows [y0, y1). */
 int orc_taa_pass(const luzw_scene_block* scene, uint32_t width, uint32_t height, const float* light_in,

@@ -58,6 +58,9 @@ def lib():
         L.orc_light_pass.restype = i32
         L.orc_light_pass.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp, u32, u32, vp, i32, u32, u32, vp, vp, u32,
                                      vp, u32, vp]
+        L.orc_light_pass_rows.restype = i32
+        L.orc_light_pass_rows.argtypes = [vp, vp, u32, u32, u32, vp, u32, vp, u32, u32, vp, i32, vp, u32, u32, u32, vp, vp,
+                                          u32, vp, u32, vp]
         L.orc_taa_pass.restype = i32
         L.orc_taa_pass.argtypes = [vp, u32, u32, vp, vp, vp, i32, u32, u32, vp]
         L.orc_volumetric_screen_pass.restype = i32
@@ -175,9 +178,16 @@ def gbuffer_pass(scene, world, models, n_models, textures, w, h, exhaustive=Fals
 
 
 def light_pass(scene, gb, frame, blue_noise, world, extra_lights=None, exhaustive=True, rows=None,
-               shadow_words=0, ao_words=0):
+               shadow_words=0, ao_words=0, row_list=None, x_range=None):
+    """light.frag over rows [rows[0], rows[1]) (default: all), or over the rows in row_list restricted to the columns
+    x_range.  exhaustive: False / 0 BVH2, True / 1 every triangle, 2 every instance box + every triangle inside.
+    Returns full-frame arrays of which only the requested pixels are written."""
     w, h = gb.w, gb.h
-    y0, y1 = rows if rows else (0, h)
+    if row_list is None:
+        y0, y1 = rows if rows else (0, h)
+        row_list = np.arange(y0, y1, dtype=np.uint32)
+    row_list = np.ascontiguousarray(row_list, np.uint32)
+    x0, x1 = x_range if x_range else (0, w)
     out = np.zeros((h, w, 4), np.float32)
     sm = np.zeros((h, w, shadow_words), np.uint32) if shadow_words else None
     am = np.zeros((h, w, ao_words), np.uint32) if ao_words else None
@@ -185,9 +195,9 @@ def light_pass(scene, gb, frame, blue_noise, world, extra_lights=None, exhaustiv
     g = gb.c()
     bn = np.ascontiguousarray(blue_noise, np.uint8)
     n_extra = len(extra_lights) if extra_lights is not None else 0
-    rc = lib().orc_light_pass(_p(scene), _p(extra_lights) if n_extra else None, n_extra, w, h, _p(g), frame, _p(bn),
-                              bn.shape[1], bn.shape[0], world.h, 1 if exhaustive else 0, y0, y1, _p(out), _p(sm),
-                              shadow_words, _p(am), ao_words, _p(st))
+    rc = lib().orc_light_pass_rows(_p(scene), _p(extra_lights) if n_extra else None, n_extra, w, h, _p(g), frame, _p(bn),
+                                   bn.shape[1], bn.shape[0], world.h, int(exhaustive), _p(row_list), row_list.size, x0, x1,
+                                   _p(out), _p(sm), shadow_words, _p(am), ao_words, _p(st))
     return rc, out, sm, am, st
 
 

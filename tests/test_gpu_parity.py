@@ -236,6 +236,77 @@ def test_gbuffer_pass_parity(rt_factory):
         assert np.array_equal(e[close], ref.emission[close])
 
 
+def test_gbuffer_pass_culls_back_faces(rt_factory):
+    """The G-buffer producer drops back-facing triangles like the Opaque Pipeline's rasteriser (cull mode BACK, front =
+    counter-clockwise): single-sided quad seen from both sides, plain and mirrored (det < 0), against the oracle, which
+    decides facing from clip coordinates."""
+    from test_oracle_kat import _culling_scene, _look_from
+    w, h = 192, 128
+    for mirror in (False, True):
+        for eye, target in (((0.0, 0.0, 5.0), (0.0, 0.0, -2.0)), ((0.0, 0.0, -9.0), (0.0, 0.0, 0.0)), ((3.0, 2.0, 4.0), (0.0, 0.0, -1.0)),
+                            ((-3.0, 1.0, -1.5), (0.0, 0.0, 0.0))):
+            sc = _culling_scene(w, h, mirror)
+            _look_from(sc, w, h, eye, target)
+            world = O.World(sc["meshes"], sc["instances"])
+            ref = O.gbuffer_pass(sc["scene"], world, sc["models"], 2, [], w, h, exhaustive=True)
+            rt = rt_factory()
+            rt.resize(w, h)
+            S.make_rt_scene(rt, sc)
+            rt.set_scene(sc["scene"])
+            rt.gbuffer_pass(sc["models"], 2)
+            a, d = rt.read(R.GBUF_ALBEDO), rt.read(R.GBUF_DEPTH)
+            same = (a[..., 0] == ref.albedo[..., 0])
+            assert same.mean() > 0.995, (mirror, eye, float(same.mean()))  # edges only
+            assert np.abs(d[same] - ref.depth[same]).max() < 2e-6
+            assert (ref.albedo[..., 0] == int(round(0.75 * 255))).any() or mirror or eye[2] < 0  # the quad is in the picture
+            rt.close()
+
+
+def test_blas_destroy_invalidates_the_tlas(rt_factory):
+    """destroying a BLAS the current TLAS points into must not leave passes traversing freed memory."""
+    rt = rt_factory()
+    sc = S.synthetic_scene(64, 32, grid=2, n_lights=1)
+    rt.resize(64, 32)
+    rt.set_blue_noise(S.blue_noise())
+    blas, inst = S.make_rt_scene(rt, sc)
+    rt.set_scene(sc["scene"])
+    rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+    rt.light_pass(0)
+    rt.blas_destroy(blas[0])
+    with pytest.raises(R.LuzError):
+        rt.light_pass(1)
+    with pytest.raises(R.LuzError):
+        rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+    # a new BLAS + an explicit "refit" request: must rebuild, then work
+    blas2 = rt.blas_create(*sc["meshes"][0], stride=48)
+    inst2 = rt.make_instances([blas2] * len(sc["instances"]), [m for (_, m, _) in sc["instances"]],
+                              [ci for (_, _, ci) in sc["instances"]])
+    rt.tlas_build(inst2, len(sc["instances"]), 1)
+    rt.light_pass(1)
+    rt.sync()
+
+
+def test_stats_without_debug_variant_ao_only_and_shadow_only(rt_factory):
+    """lit pixels / rays are reported by the product kernels too when a frame has only one kind of ray."""
+    w, h = 160, 96
+    for ls, ao in ((0, 3), (2, 0), (1, 2)):
+        rt = rt_factory()
+        sc = S.synthetic_scene(w, h, grid=3, n_lights=2, light_samples=ls, ao_samples=ao)
+        rt.resize(w, h)
+        rt.set_blue_noise(S.blue_noise())
+        S.make_rt_scene(rt, sc)
+        rt.set_scene(sc["scene"])
+        rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+        rt.set_debug(R.DEBUG_STATS)
+        rt.light_pass(3)
+        want = rt.read(R.STATS)
+        rt.set_debug(0)
+        rt.light_pass(3)
+        got = rt.read(R.STATS)
+        assert got.lit_pixels == want.lit_pixels > 0 and got.rays == want.rays == want.lit_pixels * (2 * ls + ao)
+        rt.close()
+
+
 def test_bvh_build_deterministic(rt_factory):
     """Same input => bitwise identical BLAS and TLAS across builds and contexts."""
     rng = np.random.default_rng(5)

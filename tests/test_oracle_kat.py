@@ -451,3 +451,70 @@ def test_shadow_map_lookup_known_answers():
     const = np.full((1, res, res), 0.25, np.float32)
     assert O.shadow_factor(ol, const, (0.0, 0.0, 0.9), shadow_origin=(0.0, 0.0, 0.25)) == 1.0
     assert O.shadow_factor(ol, const, (0.0, 0.0, 0.9), shadow_origin=(0.0, 0.0, 0.2499)) == 0.0
+
+
+def _culling_scene(w, h, mirror=False):
+    """One quad (two triangles, counter-clockwise seen from +z) at z = 0 in front of a unit cube at z = -4; a camera on
+    the +z side sees the quad's front, a camera on the -z side its back."""
+    sc = S.synthetic_scene(w, h, grid=1, n_lights=1, light_samples=0, ao_samples=0)
+    quad = np.zeros((4, 12), np.float32)
+    quad[:, :3] = [[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]]
+    quad[:, 3:6] = (0, 0, 1)
+    quad[:, 6:10] = (1, 0, 0, 1)
+    sc["meshes"] = [S.unit_cube(), (quad, np.array([0, 1, 2, 0, 2, 3], np.uint32))]
+    qm = S.trs((0, 0, 0), 0.0, (-1.5 if mirror else 1.5, 1.5, 1.0))
+    sc["instances"] = [(0, S.trs((0, 0, -4), 0.0, (0.5, 0.5, 0.5)), 0), (1, qm, 1)]
+    models = (wire.ModelBlock * 2)()
+    for i, (_, m, _) in enumerate(sc["instances"]):
+        S.set_mat(models[i].model_mat, m)
+        for k in range(4):
+            models[i].color[k] = 1.0
+        models[i].color[0] = 0.25 if i == 0 else 0.75
+        models[i].roughness = 0.5
+        models[i].ao_map = models[i].color_map = models[i].normal_map = -1
+        models[i].emission_map = models[i].metallic_roughness_map = -1
+    sc["models"] = models
+    return sc
+
+
+def _look_from(sc, w, h, eye, target):
+    proj = S.perspective_vk(60.0, w / h, 0.01, 1000.0)
+    view = S.look_at(eye, target)
+    sb = sc["scene"]
+    S.set_mat(sb.proj, proj.reshape(16))
+    S.set_mat(sb.view, view.reshape(16))
+    S.set_mat(sb.view_proj, S.colmajor_mul(proj, view).reshape(16))
+    S.set_mat(sb.inverse_proj, S.colmajor_inv(proj).reshape(16))
+    S.set_mat(sb.inverse_view, S.colmajor_inv(view).reshape(16))
+    for k in range(3):
+        sb.cam_pos[k] = float(eye[k])
+
+
+def test_gbuffer_back_face_culling_of_the_opaque_pipeline():
+    """The Opaque Pipeline culls back faces with counter-clockwise front faces (DeferredRenderer.cpp "Opaque Pipeline",
+    VulkanWrapper.cpp:941-946): a single-sided quad is seen from its front, is invisible from behind (the geometry
+    behind it shows), and a mirrored instance (det < 0) swaps the two."""
+    w, h = 96, 64
+    centre = (h // 2, w // 2)
+    for mirror in (False, True):
+        sc = _culling_scene(w, h, mirror)
+        world = O.World(sc["meshes"], sc["instances"])
+        seen = {}
+        for side, eye in (("front", (0.0, 0.0, 5.0)), ("back", (0.0, 0.0, -9.0))):
+            _look_from(sc, w, h, eye, (0.0, 0.0, -2.0 if side == "front" else 0.0))
+            gb = O.gbuffer_pass(sc["scene"], world, sc["models"], 2, [], w, h, exhaustive=True)
+            seen[side] = int(gb.albedo[centre][0])
+        quad, cube = int(round(0.75 * 255)), int(round(0.25 * 255))
+        # from +z: quad front (visible) unless mirrored, in which case the cube behind it shows
+        # from -z: the cube is nearer than the quad either way
+        assert seen["back"] == cube
+        assert seen["front"] == (cube if mirror else quad), (mirror, seen)
+    # seen from behind with nothing in between: the un-mirrored quad is culled, the mirrored one is visible
+    for mirror, want_hit in ((False, False), (True, True)):
+        sc = _culling_scene(w, h, mirror)
+        sc["instances"] = [sc["instances"][1]]
+        sc["instances"][0] = (1, sc["instances"][0][1], 1)
+        world = O.World(sc["meshes"], sc["instances"])
+        _look_from(sc, w, h, (0.0, 0.0, -5.0), (0.0, 0.0, 0.0))
+        gb = O.gbuffer_pass(sc["scene"], world, sc["models"], 2, [], w, h, exhaustive=True)
+        assert (gb.depth[centre] < 1.0) == want_hit, (mirror, float(gb.depth[centre]))
