@@ -81,7 +81,8 @@ def make_workload(args, rt, tmp):
     """The workload as a Luz project, loaded through the host mirror (luz_b200/workloads.py)."""
     from luz_b200 import workloads
     return workloads.Workload(rt, args.config, variant=args.variant, width=args.width, height=args.height,
-                              shadow_type=args.shadow_type, volumetric=args.volumetric, tmp=tmp)
+                              shadow_type=args.shadow_type, volumetric=args.volumetric, tmp=tmp,
+                              light_samples=args.light_samples, ao_samples=args.ao_samples)
 
 
 def blue_noise(scenes):
@@ -593,6 +594,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--ref-rows", type=int, default=0, help="rows per step of the CPU arm (0: 4 x host cores, >= 64)")
+    ap.add_argument("--light-samples", type=int, default=None, help="override lightSamples (experiments; shown in config)")
+    ap.add_argument("--ao-samples", type=int, default=None, help="override aoSamples (experiments; shown in config)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity-rows", type=int, default=64)
     args = ap.parse_args()

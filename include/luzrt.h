@@ -78,7 +78,9 @@ enum {
     LUZRT_GBUF_EMISSION = 8,/* RGBA8                                                          */
     LUZRT_GBUF_DEPTH = 9,   /* F32                                                            */
     LUZRT_IMG_COMPOSE = 10, /* BGRA8 from luzrt_compose_pass                                  */
-    LUZRT_TIMINGS = 11      /* luzrt_timings of the last frame (CUDA events, ms)              */
+    LUZRT_TIMINGS = 11,     /* luzrt_timings of the last frame (CUDA events, ms)              */
+    LUZRT_STATS_DETAIL = 12 /* uint64[40]: per ray class break-down of the last light pass run with LUZRT_DEBUG_STATS
+                               (layout: csrc/common.cuh DeviceStats::detail; measurement aid, profiles/)   */
 };
 
 /* luzrt_set_debug flags */

@@ -1056,6 +1056,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.ao_words = (uint32_t)c->ao_mask_words;
     a.stats = c->d_stats;
     a.lit_counters = c->d_lit;
+    a.tile_counter = reinterpret_cast<uint32_t*>(c->d_lit + 8); // a spare word of the counter block (only every 16th u64 counts)
     a.shadow_maps = c->d_shadow_recs;
     a.hints = nullptr;
     static const bool hints_env = [] { // LUZRT_SHADOW_HINTS=0: no occluder hints (tuning / A-B runs)
@@ -1310,6 +1311,12 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
     DeviceGuard g(c->device);
     CU(c, wait_gather(c));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (which == LUZRT_STATS_DETAIL) {
+        REQUIRE(c, bytes >= sizeof(unsigned long long) * 40, "buffer too small for the 40 detail counters");
+        CU(c, cudaMemcpy(dst, reinterpret_cast<const char*>(c->d_stats) + offsetof(DeviceStats, detail),
+                         sizeof(unsigned long long) * 40, cudaMemcpyDeviceToHost));
+        return LUZRT_OK;
+    }
     if (which == LUZRT_STATS) {
         REQUIRE(c, bytes >= sizeof(luzrt_stats), "buffer too small for luzrt_stats");
         DeviceStats ds{};

@@ -117,6 +117,12 @@ struct BandSet {
 
 struct DeviceStats {
     unsigned long long lit_pixels, rays, nodes, tris, insts, occluded;
+    // LUZRT_STATS_DETAIL (statistics variant only): per ray class c in {0 hinted shadow, 1 unhinted shadow, 2 AO with a
+    // candidate list, 3 AO descending from the root} detail[8 c + {0 rays, 1 occluded, 2 TLAS nodes, 3 BLAS nodes,
+    // 4 triangles, 5 instances entered, 6 root descents, 7 unused}]; detail[32..] = {AO pixels, AO pixels with an empty
+    // list, AO pixels whose list overflowed, candidates kept, nodes of the per-pixel box queries + filters, hint rays,
+    // hint rays that hit}
+    unsigned long long detail[40];
 };
 
 // ---- small vector helpers ------------------------------------------------------------------

@@ -192,6 +192,10 @@ __global__ void __launch_bounds__(128) k_shadow_hints(const LightArgs a, uint32_
             uint2 stack[LUZ_STACK_SIZE];
             HitInfo h;
             if (trace_ray<false, STATS>(a.scene, O, rg_normalize(C), 0.001f, rg_length(C), &h, &st, stack)) hint = h.inst;
+            if (STATS) {
+                atomicAdd(&a.stats->detail[37], 1ull);
+                if (hint != kNoInstance) atomicAdd(&a.stats->detail[38], 1ull);
+            }
         }
         hints[(size_t)tile * (uint32_t)fc.num_lights + light] = hint;
     }
@@ -242,6 +246,9 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
 
     uint2 stack[LUZ_STACK_SIZE];
     LocalStats st = {0, 0, 0};
+    uint32_t det[40]; // STATS: per-class detail, see DeviceStats
+    if (STATS)
+        for (int k = 0; k < 40; k++) det[k] = 0;
     uint32_t n_rays = 0, n_occl = 0;
     const uint32_t counted = (r >= a.count_row_begin && r < a.count_row_end) ? 1u : 0u; // halo rows are recomputation
     BitWriter bits; // the shadow bits of all lights in light order, then (restarted) the AO bits
@@ -284,8 +291,16 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
                         // then the same argument in the object space of every candidate against its BLAS root
                         float3 lo, hi;
                         hemisphere_box(O, T, B, C, m, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                        const uint32_t nodes0 = st.nodes;
                         n_cand = collect_instances<STATS>(a.scene, lo, hi, s_cand, 128, kMaxCand, stack, &st);
                         if (n_cand > 0) n_cand = filter_candidates<STATS>(a.scene, O, T, B, C, m, s_cand, 128, n_cand, &st);
+                        if (STATS && counted) {
+                            det[32]++;
+                            det[33] += n_cand == 0;
+                            det[34] += n_cand < 0;
+                            det[35] += (uint32_t)max(n_cand, 0);
+                            det[36] += st.nodes - nodes0;
+                        }
                     } else {
                         const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
                                               m * sqrtf(T.y * T.y + B.y * B.y + C.y * C.y) + 1e-6f,
@@ -330,7 +345,21 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
                     dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
                 }
                 n_rays += counted;
-                const bool hit = trace_ray<false, STATS, false, ONE_VISIT>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, &st, stack, s_cand, 128, n_cand, hinted);
+                LocalStats rst = {0, 0, 0};
+                const bool hit = trace_ray<false, STATS, false, ONE_VISIT>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, STATS ? &rst : &st, stack, s_cand, 128, n_cand, hinted);
+                if (STATS) {
+                    st.nodes += rst.nodes, st.tris += rst.tris, st.insts += rst.insts;
+                    if (counted) {
+                        uint32_t* d8 = det + 8 * (is_ao ? (n_cand > 0 ? 2 : 3) : (hinted ? 0 : 1));
+                        d8[0]++;
+                        d8[1] += hit;
+                        d8[2] += rst.tlas_nodes;
+                        d8[3] += rst.nodes - rst.tlas_nodes;
+                        d8[4] += rst.tris;
+                        d8[5] += rst.insts;
+                        d8[6] += rst.root_descents;
+                    }
+                }
                 n_occl += hit ? counted : 0u;
                 bits.push(hit);
             }
@@ -352,6 +381,11 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
             atomicAdd(&a.stats->tris, vals[2]);
             atomicAdd(&a.stats->insts, vals[3]);
             atomicAdd(&a.stats->occluded, vals[4]);
+        }
+        for (int k = 0; k < 37; k++) {
+            unsigned long long vsum = det[k];
+            for (int off = 16; off; off >>= 1) vsum += __shfl_xor_sync(0xFFFFFFFFu, vsum, off);
+            if (lane == 0 && vsum) atomicAdd(&a.stats->detail[k], vsum);
         }
     }
 }
@@ -378,6 +412,245 @@ __global__ void __launch_bounds__(128, 6) k_light_rays_split(const LightArgs a) 
         light_rays_body<false, 0, ONE_VISIT>(a, blockIdx.z);
     else
         light_rays_body<false, 1, ONE_VISIT>(a, blockIdx.z - a.rows.n_bands);
+}
+
+// ---- the ray kernel hosts get: persistent warps, per-warp ray queue with ballot compaction -------------------------
+// The kernels above give every pixel a lane and let the lane fire its rays one after the other.  Measured on C3
+// (profiles/r2_ray_classes.md, r1_light_rays_v7.md): 15 of 32 lanes active per instruction -- 71 % of the pixels hold
+// an empty AO candidate list and sit idle while their neighbours trace 16 rays, a fifth of the hinted shadow rays miss
+// the hinted instance and descend from the TLAS root at a fifth of a warp, and partly lit tiles never fill a warp.
+// Here the lanes of a warp only PRODUCE rays for their pixel (one round = one (light, sample) or one AO sample for
+// every lane that has one); a produced ray goes into a queue in shared memory at the position ballot + prefix popcount
+// give it, and whenever the queue holds 32 rays the warp DRAINS one batch: lane i traces ray i of the batch, whoever
+// produced it.  A hinted shadow ray that misses its hinted instance is put back as a root ray, so the expensive TLAS
+// descents are traced 32 at a time as well.  Results travel by atomic OR into the pixel's mask word (the kernel clears
+// the words of its tile first, so there is no separate memset pass over the frame).  Warps pull 8x4-pixel tiles from an
+// atomic counter: a launch has no tail, whatever share of the frame a rank owns.
+//   item = {O.xyz, tmax | dir.xyz, meta | aux};  meta: bits 0-4 owner lane, 5-6 kind, 7 AO mask, 8.. bit in the mask
+// Any-hit visibility does not depend on which lane traces a ray or in which order occluders are tried: the bits are
+// identical to the kernels above (tests/test_gpu_parity.py run_light asserts it on every parity scene).
+constexpr int kQueueCap = 64; // < 32 before a production round, + 32 produced; a drain pops 32 and re-queues <= 32
+enum : uint32_t { kKindRoot = 0u, kKindHinted = 1u, kKindList = 2u };
+
+struct __align__(16) WarpQueue {
+    float4 q0[kQueueCap]; // O.xyz, tmax
+    float4 q1[kQueueCap]; // dir.xyz, meta
+    uint32_t aux[kQueueCap];       // kKindHinted: the hinted instance
+    uint32_t cand[kMaxCand * 32];  // AO candidate lists [k][lane]
+    int n_cand[32];
+};
+
+template <bool ONE_VISIT>
+__global__ void __launch_bounds__(128, 6) k_light_rays_queue(const LightArgs a, uint32_t* __restrict__ tile_counter,
+                                                             const uint32_t tiles_x, const uint32_t tiles_y,
+                                                             const uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpQueue& ws = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const uint32_t hints_x = (fc.width + 15u) / 16u, hints_y = (a.rows.rows + 7u) / 8u;
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const bool shadows = fc.shadow_type == LUZW_SHADOW_RAYTRACING && fc.num_lights > 0;
+    uint2 stack[LUZ_STACK_SIZE];
+
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t bx = t % tiles_x, by = (t / tiles_x) % tiles_y, band = t / (tiles_x * tiles_y);
+        const uint32_t x = bx * 8u + (lane & 7), r = by * 4u + (lane >> 3);
+        const bool in_image = x < fc.width && r < a.rows.rows;
+        const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
+        const size_t pix = (size_t)y * fc.width + x;
+
+        float3 N = f3(0.0f, 0.0f, 0.0f);
+        float depth = 1.0f;
+        uchar4 bn8 = make_uchar4(0, 0, 0, 0);
+        if (in_image) {
+            const float4 n4 = __ldg(a.normal + pix);
+            N = f3(n4.x, n4.y, n4.z);
+            depth = __ldg(a.depth + pix);
+            bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+            for (uint32_t w = 0; w < a.shadow_words; w++) a.shadow_mask[pix * a.shadow_words + w] = 0u;
+            for (uint32_t w = 0; w < a.ao_words; w++) a.ao_mask[pix * a.ao_words + w] = 0u;
+        }
+        const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
+        __syncwarp(); // the cleared words are visible to whichever lane ORs a result into them
+        if (!__any_sync(0xFFFFFFFFu, lit)) continue;
+        const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+        const float3 fragPos = depth_to_world(fc, u, v, depth);
+        const float camDist = length3(fragPos - camPos);
+        const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+        const uint32_t hint_tile = (band * hints_y + (r >> 3)) * hints_x + (x >> 4);
+
+        // production state: phase 0 = shadow rounds over (light, sample), 1 = AO candidate lists, 2 = AO rounds, 3 = done
+        int phase = shadows ? 0 : 1, light = 0, sample = 0;
+        uint32_t bit0 = 0; // first mask bit of the current light
+        bool ao_active = false;
+        int q_count = 0;
+
+        while (true) {
+            // ---- produce rounds until a batch is ready (or nothing is left to produce) ----
+            while (q_count < 32 && phase < 3) {
+                if (phase == 0) {
+                    if (light >= fc.num_lights) {
+                        phase = 1;
+                        continue;
+                    }
+                    const float4* lp = reinterpret_cast<const float4*>(a.lights + light); // same address in every lane
+                    LightRec L4;
+                    reinterpret_cast<float4*>(&L4)[0] = __ldg(lp + 0);
+                    reinterpret_cast<float4*>(&L4)[1] = __ldg(lp + 1);
+                    reinterpret_cast<float4*>(&L4)[2] = __ldg(lp + 2);
+                    reinterpret_cast<float4*>(&L4)[3] = __ldg(lp + 3);
+                    const int n_samples = L4.num_shadow_samples;
+                    if (sample >= n_samples) { // no rays, no bits (light.frag:87-89)
+                        bit0 += (uint32_t)max(n_samples, 0);
+                        light++;
+                        sample = 0;
+                        continue;
+                    }
+                    uint32_t hint = kNoInstance;
+                    if (a.hints && lit) hint = __ldg(a.hints + (size_t)hint_tile * (uint32_t)fc.num_lights + (uint32_t)light);
+                    float3 O = f3(0.0f, 0.0f, 0.0f), dir = O;
+                    float tMaxRay = 0.0f;
+                    if (lit) { // EvaluateShadow + TraceShadowRay (light.frag:137-146, :86-100)
+                        float3 C;
+                        shadow_ray_frame(L4, fragPos, N, camDist, O, C);
+                        const float3 T = rg_normalize(cross3(C, f3(0.0f, 1.0f, 0.0f)));
+                        const float3 B = rg_normalize(cross3(T, C));
+                        tMaxRay = rg_length(C);
+                        const float2 rng = blue_noise_sample(bn_r, bn_g, sample, fc.frame_mod);
+                        const float pointRadius = L4.radius * rg_sqrt(rng.x); // DiskSample (light.frag:57-61)
+                        float sn, cs;
+                        rg_sincos(rng.y * 2.0f * kPI, &sn, &cs);
+                        dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
+                    }
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, lit);
+                    if (lit) {
+                        const int pos = q_count + __popc(m & lt_mask);
+                        const uint32_t kind = hint != kNoInstance ? kKindHinted : kKindRoot;
+                        const uint32_t meta = (uint32_t)lane | (kind << 5) | ((bit0 + (uint32_t)sample) << 8);
+                        ws.q0[pos] = make_float4(O.x, O.y, O.z, tMaxRay);
+                        ws.q1[pos] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(meta));
+                        ws.aux[pos] = hint;
+                    }
+                    q_count += __popc(m);
+                    sample++;
+                } else if (phase == 1) { // TraceAORays (light.frag:111-135): the per-pixel candidate lists
+                    const int n_samples = fc.ao_num_samples;
+                    if (n_samples <= 0) {
+                        phase = 3;
+                        continue;
+                    }
+                    int n_cand = -1; // < 0: the rays descend from the TLAS root
+                    if (lit && n_samples >= kMinCandSamples) {
+                        const float3 O = fragPos + N * (camDist * 0.01f);
+                        const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+                        const float3 B = cross3(N, T);
+                        const float mreach = fabsf(fc.ao_max) * 1.001f;
+                        if (LUZ_AO_HEMISPHERE && fc.ao_min >= 0.0f && fc.ao_max >= 0.0f) {
+                            float3 lo, hi;
+                            hemisphere_box(O, T, B, N, mreach, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                            n_cand = collect_instances<false>(a.scene, lo, hi, ws.cand + lane, 32, kMaxCand, stack, nullptr);
+                            if (n_cand > 0) n_cand = filter_candidates<false>(a.scene, O, T, B, N, mreach, ws.cand + lane, 32, n_cand, nullptr);
+                        } else {
+                            const float3 ext = f3(mreach * sqrtf(T.x * T.x + B.x * B.x + N.x * N.x) + 1e-6f,
+                                                  mreach * sqrtf(T.y * T.y + B.y * B.y + N.y * N.y) + 1e-6f,
+                                                  mreach * sqrtf(T.z * T.z + B.z * B.z + N.z * N.z) + 1e-6f);
+                            n_cand = collect_instances<false>(a.scene, O - ext, O + ext, ws.cand + lane, 32, kMaxCand, stack, nullptr);
+                        }
+                    }
+                    ws.n_cand[lane] = n_cand;
+                    ao_active = lit && n_cand != 0; // an empty list: every AO ray of the pixel misses, no bit is set
+                    sample = 0;
+                    phase = __any_sync(0xFFFFFFFFu, ao_active) ? 2 : 3;
+                    __syncwarp();
+                } else { // phase 2: one AO sample of every pixel that has occluders within reach
+                    if (sample >= fc.ao_num_samples) {
+                        phase = 3;
+                        continue;
+                    }
+                    float3 O = f3(0.0f, 0.0f, 0.0f), dir = O;
+                    if (ao_active) { // HemisphereSample (light.frag:63-69); the frame is cheap to rebuild per round
+                        O = fragPos + N * (camDist * 0.01f);
+                        const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+                        const float3 B = cross3(N, T);
+                        const float2 rng = blue_noise_sample(bn_r, bn_g, sample, fc.frame_mod);
+                        const float rr = rg_sqrt(rng.x);
+                        float sn, cs;
+                        rg_sincos(6.283f * rng.y, &sn, &cs);
+                        dir = rg_combine(T, rr * cs, B, rr * sn, N, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
+                    }
+                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ao_active);
+                    if (ao_active) {
+                        const int pos = q_count + __popc(m & lt_mask);
+                        const uint32_t kind = ws.n_cand[lane] > 0 ? kKindList : kKindRoot;
+                        const uint32_t meta = (uint32_t)lane | (kind << 5) | 0x80u | ((uint32_t)sample << 8);
+                        ws.q0[pos] = make_float4(O.x, O.y, O.z, fc.ao_max);
+                        ws.q1[pos] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(meta));
+                    }
+                    q_count += __popc(m);
+                    sample++;
+                }
+                __syncwarp();
+            }
+            if (q_count == 0) break; // nothing queued, nothing left to produce
+
+            // ---- drain one batch: the newest (most coherent) rays first ----
+            const int n = min(q_count, 32);
+            q_count -= n;
+            const bool valid = lane < n;
+            float4 i0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), i1 = i0;
+            uint32_t aux = 0;
+            if (valid) {
+                i0 = ws.q0[q_count + lane];
+                i1 = ws.q1[q_count + lane];
+                aux = ws.aux[q_count + lane];
+            }
+            __syncwarp(); // every item is in registers before the slots are reused
+            bool again = false;
+            const uint32_t meta = __float_as_uint(i1.w);
+            if (valid) {
+                const uint32_t owner = meta & 31u, kind = (meta >> 5) & 3u;
+                const bool is_ao = (meta & 0x80u) != 0u;
+                const uint32_t* cand = nullptr;
+                int stride = 0, n_cand = -1;
+                if (kind == kKindHinted) {
+                    cand = &aux; // a one-entry list in a register-backed local
+                    n_cand = 1;
+                } else if (kind == kKindList) {
+                    cand = ws.cand + owner;
+                    stride = 32;
+                    n_cand = ws.n_cand[owner];
+                }
+                const bool hit = trace_ray<false, false, false, ONE_VISIT>(a.scene, f3(i0.x, i0.y, i0.z), f3(i1.x, i1.y, i1.z),
+                                                                           is_ao ? fc.ao_min : 0.001f, i0.w, nullptr, nullptr, stack,
+                                                                           cand, stride, n_cand, false);
+                if (hit) {
+                    const uint32_t ox = bx * 8u + (owner & 7u), orow = by * 4u + (owner >> 3);
+                    const size_t opix = (size_t)band_row(fc, a.rows, band, orow) * fc.width + ox;
+                    const uint32_t bit = meta >> 8;
+                    uint32_t* word = is_ao ? a.ao_mask + opix * a.ao_words + (bit >> 5) : a.shadow_mask + opix * a.shadow_words + (bit >> 5);
+                    atomicOr(word, 1u << (bit & 31u));
+                } else if (kind == kKindHinted) {
+                    again = true; // the hinted instance does not occlude it: back into the queue as a root ray
+                }
+            }
+            const uint32_t am = __ballot_sync(0xFFFFFFFFu, again);
+            if (am) {
+                if (again) {
+                    const int pos = q_count + __popc(am & lt_mask);
+                    ws.q0[pos] = i0;
+                    ws.q1[pos] = make_float4(i1.x, i1.y, i1.z, __uint_as_float(meta & ~(3u << 5)));
+                }
+                q_count += __popc(am);
+                __syncwarp();
+            }
+        }
+    }
 }
 
 // ---- kernel 2: shading -----------------------------------------------------------------------------------------
@@ -505,16 +778,14 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
     const size_t px = (size_t)args.fc.width * args.fc.height;
     cudaError_t e;
-    if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
     // which ray kernel: the plain one (every ray of a pixel in one CTA) for the statistics variant and when forced by
     // LUZRT_RAY_KERNEL=plain; otherwise the specialised bodies (split when both kinds of ray exist)
-    static const int kernel_env = [] { // 0 auto, 1 plain
+    static const int kernel_env = [] { // 0 auto (persistent warps + ray queue), 1 plain, 2 the per-pixel specialised kernels
         const char* e2 = getenv("LUZRT_RAY_KERNEL");
-        return (e2 && e2[0] == 'p') ? 1 : 0;
+        return (e2 && e2[0] == 'p') ? 1 : (e2 && e2[0] == 's') ? 2 : 0;
     }();
     static const int one_visit_env = [] { // 0: the yielding node loop in the specialised kernels (tuning runs; the `if` form is 2-3 % faster there)
         const char* e2 = getenv("LUZRT_ONE_VISIT");
@@ -522,9 +793,14 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     }();
     const bool any_shadow = args.fc.shadow_type == LUZW_SHADOW_RAYTRACING && args.fc.num_lights > 0;
     const bool any_ao = args.fc.ao_num_samples > 0;
-    const bool plain = stats || kernel_env == 1 || (!any_shadow && !any_ao);
-    const bool split = !plain && any_shadow && any_ao;
+    const bool queue = !stats && kernel_env == 0 && (any_shadow || any_ao);
+    const bool plain = !queue && (stats || kernel_env == 1 || (!any_shadow && !any_ao));
+    const bool split = !queue && !plain && any_shadow && any_ao;
     const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands * (split ? 2u : 1u));
+    if (!queue) { // the queue kernel clears the mask words of the tiles it shades itself
+        if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
+    }
     if (any_shadow && args.hints) { // one hint ray per tile and light
         const uint32_t n = grid.x * grid.y * args.rows.n_bands * (uint32_t)args.fc.num_lights;
         if (stats)
@@ -539,7 +815,21 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         const char* e2 = getenv("LUZRT_LIGHT_MINB");
         return e2 ? atoi(e2) : 6;
     }();
-    if (split) {
+    if (queue) {
+        static int blocks = 0;
+        if (!blocks) {
+            int dev = 0, sms = 0, per_sm = 0;
+            if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+            if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+            if ((e = cudaFuncSetAttribute(k_light_rays_queue<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpQueue)))) != cudaSuccess) return e;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_light_rays_queue<true>, 128, 4 * sizeof(WarpQueue))) != cudaSuccess) return e;
+            blocks = sms * max(per_sm, 1);
+        }
+        const uint32_t tx = (args.fc.width + 7) / 8, ty = (args.rows.rows + 3) / 4;
+        const uint32_t n_tiles = tx * ty * args.rows.n_bands;
+        if ((e = cudaMemsetAsync(args.tile_counter, 0, sizeof(uint32_t), stream)) != cudaSuccess) return e;
+        k_light_rays_queue<true><<<min((uint32_t)blocks, (n_tiles + 3) / 4), 128, 4 * sizeof(WarpQueue), stream>>>(a2, args.tile_counter, tx, ty, n_tiles);
+    } else if (split) {
         if (one_visit_env == 0)
             k_light_rays_split<false><<<grid, 128, smem, stream>>>(a2);
         else

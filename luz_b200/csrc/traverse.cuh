@@ -24,6 +24,7 @@ struct HitInfo {
 
 struct LocalStats {
     uint32_t nodes, tris, insts;
+    uint32_t tlas_nodes, root_descents; // of `nodes`: visited in the TLAS; descents from the TLAS root started
 };
 
 // Reciprocal for slab tests: one MUFU.RCP (relative error <= 2^-23) instead of the ~10-instruction IEEE
@@ -390,6 +391,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     float face_sign = 0.0f; // FACE_CULL: cull_sign * sign(det of the current instance's matrix)
     float3 widir; // candidate mode keeps the world-space reciprocal direction for the box pre-test below
     if (from_root) {
+        if (STATS) st->root_descents++;
         rs = make_ray_space(o, d);
         widir = rs.idir;
         ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
@@ -440,7 +442,10 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
             const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
             const WideNode* node = nodes + (ngroup.x + rel);
             const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(node));
-            if (STATS) st->nodes++;
+            if (STATS) {
+                st->nodes++;
+                if (inst_sp < 0) st->tlas_nodes++;
+            }
             const uint32_t slots = intersect_node(node, rs, tmin, tmax);
             const uint32_t node_imask = hdr.x >> 24;
             ngroup = make_uint2(hdr.x & 0x00FFFFFFu, ((slots & node_imask) << 24) | node_imask);
@@ -522,6 +527,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 }
                 if (pending != kNoInstance) continue;
                 if (then_root && !from_root) { // none of the hinted instances was hit: the ordinary descent
+                    if (STATS) st->root_descents++;
                     from_root = true;
                     o = wo;
                     d = wd;

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libluzrt.so")
 # luzrt_read selectors
 IMG_LIGHT, IMG_HISTORY, SHADOW_MASK, AO_MASK, STATS = 0, 1, 2, 3, 4
 GBUF_ALBEDO, GBUF_NORMAL, GBUF_MATERIAL, GBUF_EMISSION, GBUF_DEPTH, IMG_COMPOSE, TIMINGS = 5, 6, 7, 8, 9, 10, 11
+STATS_DETAIL = 12
 DEBUG_MASKS, DEBUG_STATS, DEBUG_NO_HINTS = 1, 2, 4
 
 EXPORTS = [
@@ -304,6 +305,10 @@ class LuzRT:
             s = wire.Stats()
             self._ck(self.lib.luzrt_read(self.h, which, _ptr(s), C.sizeof(s)))
             return s
+        elif which == STATS_DETAIL:
+            d = np.zeros(40, np.uint64)
+            self._ck(self.lib.luzrt_read(self.h, which, _ptr(d), d.nbytes))
+            return d
         elif which == TIMINGS:
             t = wire.Timings()
             self._ck(self.lib.luzrt_read(self.h, which, _ptr(t), C.sizeof(t)))

@@ -12,7 +12,8 @@ from . import scenes
 
 
 class Workload:
-    def __init__(self, rt, config, variant=None, width=0, height=0, shadow_type=1, volumetric=0, tmp=None):
+    def __init__(self, rt, config, variant=None, width=0, height=0, shadow_type=1, volumetric=0, tmp=None,
+                 light_samples=None, ao_samples=None):
         self.rt, self.config, self.variant = rt, config, variant
         self.tmp = tmp or tempfile.mkdtemp(prefix="luzwork_")
         path, bin_path, cfg = scenes.write_project(config, self.tmp, variant)
@@ -35,6 +36,10 @@ class Workload:
                 json.dump(doc, f)
         if width:
             cfg["width"], cfg["height"] = width, height
+        if light_samples is not None:  # experiments (profiles/): one kind of ray only
+            cfg["light_samples"] = light_samples
+        if ao_samples is not None:
+            cfg["ao_samples"] = ao_samples
         self.cfg = cfg
         self.width, self.height = cfg["width"], cfg["height"]
         self.app = H.LuzHost(rt)
