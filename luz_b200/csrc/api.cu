@@ -1077,9 +1077,8 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
     CU(c, cudaEventRecord(c->ev[EV_LIGHT_RAYS][0], c->stream));
-    CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1]));
+    CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1], &c->launches));
     c->ev_valid[EV_LIGHT_RAYS] = true;
-    c->launches += a.hints ? 3 : 2;
     ev_end(c, EV_LIGHT);
     return LUZRT_OK;
 }

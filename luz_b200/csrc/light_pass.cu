@@ -414,41 +414,16 @@ __global__ void __launch_bounds__(128, 6) k_light_rays_split(const LightArgs a) 
         light_rays_body<false, 1, ONE_VISIT>(a, blockIdx.z - a.rows.n_bands);
 }
 
-// ---- the ray kernel hosts get: persistent warps, per-warp ray queue with ballot compaction -------------------------
-// The kernels above give every pixel a lane and let the lane fire its rays one after the other.  Measured on C3
-// (profiles/r2_ray_classes.md, r1_light_rays_v7.md): 15 of 32 lanes active per instruction -- 71 % of the pixels hold
-// an empty AO candidate list and sit idle while their neighbours trace 16 rays, a fifth of the hinted shadow rays miss
-// the hinted instance and descend from the TLAS root at a fifth of a warp, and partly lit tiles never fill a warp.
-// Here the lanes of a warp only PRODUCE rays for their pixel (one round = one (light, sample) or one AO sample for
-// every lane that has one); a produced ray goes into a queue in shared memory at the position ballot + prefix popcount
-// give it, and whenever the queue holds 32 rays the warp DRAINS one batch: lane i traces ray i of the batch, whoever
-// produced it.  A hinted shadow ray that misses its hinted instance is put back as a root ray, so the expensive TLAS
-// descents are traced 32 at a time as well.  Results travel by atomic OR into the pixel's mask word (the kernel clears
-// the words of its tile first, so there is no separate memset pass over the frame).  Warps pull 8x4-pixel tiles from an
-// atomic counter: a launch has no tail, whatever share of the frame a rank owns.
-//   item = {O.xyz, tmax | dir.xyz, meta | aux};  meta: bits 0-4 owner lane, 5-6 kind, 7 AO mask, 8.. bit in the mask
-// Any-hit visibility does not depend on which lane traces a ray or in which order occluders are tried: the bits are
-// identical to the kernels above (tests/test_gpu_parity.py run_light asserts it on every parity scene).
-constexpr int kQueueCap = 64; // < 32 before a production round, + 32 produced; a drain pops 32 and re-queues <= 32
-enum : uint32_t { kKindRoot = 0u, kKindHinted = 1u, kKindList = 2u };
-
-struct __align__(16) WarpQueue {
-    float4 q0[kQueueCap]; // O.xyz, tmax
-    float4 q1[kQueueCap]; // dir.xyz, meta
-    uint32_t aux[kQueueCap];       // kKindHinted: the hinted instance
-    uint32_t cand[kMaxCand * 32];  // AO candidate lists [k][lane]
-    int n_cand[32];
-};
-
-template <bool ONE_VISIT>
-__global__ void __launch_bounds__(128, 6) k_light_rays_queue(const LightArgs a, uint32_t* __restrict__ tile_counter,
-                                                             const uint32_t tiles_x, const uint32_t tiles_y,
-                                                             const uint32_t n_tiles) {
+// ---- persistent warps, every ray per lane (the body above inside a tile loop) -----------------------------------------
+// PART 0: the shadow rays, 1: the AO rays (two launches, each body specialised at compile time); -1: both in one launch.
+template <bool ONE_VISIT, int MIN_BLOCKS, int PART>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const LightArgs a, uint32_t* __restrict__ tile_counter,
+                                                                           const uint32_t tiles_x, const uint32_t tiles_y,
+                                                                           const uint32_t n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const FrameConst& fc = a.fc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpQueue& ws = reinterpret_cast<WarpQueue*>(smem_raw)[warp];
-    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw) + warp * (kMaxCand * 32) + lane; // candidate lists [k][lane]
     const uint32_t hints_x = (fc.width + 15u) / 16u, hints_y = (a.rows.rows + 7u) / 8u;
     const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
     const bool shadows = fc.shadow_type == LUZW_SHADOW_RAYTRACING && fc.num_lights > 0;
@@ -464,7 +439,6 @@ __global__ void __launch_bounds__(128, 6) k_light_rays_queue(const LightArgs a, 
         const bool in_image = x < fc.width && r < a.rows.rows;
         const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
         const size_t pix = (size_t)y * fc.width + x;
-
         float3 N = f3(0.0f, 0.0f, 0.0f);
         float depth = 1.0f;
         uchar4 bn8 = make_uchar4(0, 0, 0, 0);
@@ -473,183 +447,100 @@ __global__ void __launch_bounds__(128, 6) k_light_rays_queue(const LightArgs a, 
             N = f3(n4.x, n4.y, n4.z);
             depth = __ldg(a.depth + pix);
             bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
-            for (uint32_t w = 0; w < a.shadow_words; w++) a.shadow_mask[pix * a.shadow_words + w] = 0u;
-            for (uint32_t w = 0; w < a.ao_words; w++) a.ao_mask[pix * a.ao_words + w] = 0u;
+            if (PART != 1)
+                for (uint32_t w = 0; w < a.shadow_words; w++) a.shadow_mask[pix * a.shadow_words + w] = 0u;
+            if (PART != 0)
+                for (uint32_t w = 0; w < a.ao_words; w++) a.ao_mask[pix * a.ao_words + w] = 0u;
         }
         const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
-        __syncwarp(); // the cleared words are visible to whichever lane ORs a result into them
-        if (!__any_sync(0xFFFFFFFFu, lit)) continue;
-        const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
-        const float3 fragPos = depth_to_world(fc, u, v, depth);
-        const float camDist = length3(fragPos - camPos);
-        const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
-        const uint32_t hint_tile = (band * hints_y + (r >> 3)) * hints_x + (x >> 4);
-
-        // production state: phase 0 = shadow rounds over (light, sample), 1 = AO candidate lists, 2 = AO rounds, 3 = done
-        int phase = shadows ? 0 : 1, light = 0, sample = 0;
-        uint32_t bit0 = 0; // first mask bit of the current light
-        bool ao_active = false;
-        int q_count = 0;
-
-        while (true) {
-            // ---- produce rounds until a batch is ready (or nothing is left to produce) ----
-            while (q_count < 32 && phase < 3) {
-                if (phase == 0) {
-                    if (light >= fc.num_lights) {
-                        phase = 1;
-                        continue;
+        if (lit) {
+            const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+            const float3 fragPos = depth_to_world(fc, u, v, depth);
+            const float camDist = length3(fragPos - camPos);
+            const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+            const size_t hint_base = (size_t)((band * hints_y + (by >> 1)) * hints_x + (bx >> 1)) * (uint32_t)fc.num_lights;
+            BitWriter bits;
+            bits.words = a.shadow_mask + pix * a.shadow_words;
+            // one loop over the ray sources (the lights, then AO) so that the kernel holds one inlined copy of the traversal
+            const int li_first = (PART == 1 || !shadows) ? fc.num_lights : 0;
+            const int li_last = PART == 0 ? fc.num_lights - 1 : fc.num_lights;
+            for (int li = li_first; li <= li_last; li++) {
+                const bool is_ao = PART == 1 || (PART < 0 && li == fc.num_lights);
+                float3 O, T, B, C;
+                float radius = 0.0f, tMinRay, tMaxRay;
+                int n_samples, n_cand = -1;
+                bool hinted = false;
+                if (is_ao) { // TraceAORays (light.frag:111-135)
+                    bits.flush();
+                    n_samples = fc.ao_num_samples;
+                    if (n_samples <= 0) break;
+                    bits.words = a.ao_mask + pix * a.ao_words;
+                    bits.bit = 0;
+                    O = fragPos + N * (camDist * 0.01f);
+                    T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+                    B = cross3(N, T);
+                    C = N;
+                    tMinRay = fc.ao_min;
+                    tMaxRay = fc.ao_max;
+                    if (n_samples >= kMinCandSamples) {
+                        const float m = fabsf(tMaxRay) * 1.001f;
+                        if (LUZ_AO_HEMISPHERE && tMinRay >= 0.0f && tMaxRay >= 0.0f) {
+                            float3 lo, hi;
+                            hemisphere_box(O, T, B, C, m, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                            n_cand = collect_instances<false>(a.scene, lo, hi, s_cand, 32, kMaxCand, stack, nullptr);
+                            if (n_cand > 0) n_cand = filter_candidates<false>(a.scene, O, T, B, C, m, s_cand, 32, n_cand, nullptr);
+                        } else {
+                            const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + C.x * C.x) + 1e-6f,
+                                                  m * sqrtf(T.y * T.y + B.y * B.y + C.y * C.y) + 1e-6f,
+                                                  m * sqrtf(T.z * T.z + B.z * B.z + C.z * C.z) + 1e-6f);
+                            n_cand = collect_instances<false>(a.scene, O - ext, O + ext, s_cand, 32, kMaxCand, stack, nullptr);
+                        }
                     }
-                    const float4* lp = reinterpret_cast<const float4*>(a.lights + light); // same address in every lane
+                    if (n_cand == 0) break; // no instance within reach of any AO ray of this pixel: every one of them misses
+                } else { // EvaluateShadow + TraceShadowRay (light.frag:137-146, :86-109)
+                    const float4* lp = reinterpret_cast<const float4*>(a.lights + li); // same address in every lane
                     LightRec L4;
                     reinterpret_cast<float4*>(&L4)[0] = __ldg(lp + 0);
                     reinterpret_cast<float4*>(&L4)[1] = __ldg(lp + 1);
                     reinterpret_cast<float4*>(&L4)[2] = __ldg(lp + 2);
                     reinterpret_cast<float4*>(&L4)[3] = __ldg(lp + 3);
-                    const int n_samples = L4.num_shadow_samples;
-                    if (sample >= n_samples) { // no rays, no bits (light.frag:87-89)
-                        bit0 += (uint32_t)max(n_samples, 0);
-                        light++;
-                        sample = 0;
-                        continue;
+                    n_samples = L4.num_shadow_samples;
+                    if (n_samples <= 0) continue; // no rays, no bits (light.frag:87-89)
+                    radius = L4.radius;
+                    shadow_ray_frame(L4, fragPos, N, camDist, O, C);
+                    if (a.hints) { // the tile's occluder hint for this light is tried first (see k_shadow_hints)
+                        const uint32_t hint = __ldg(a.hints + hint_base + (uint32_t)li);
+                        if (hint != kNoInstance) {
+                            s_cand[0] = hint;
+                            n_cand = 1;
+                            hinted = true;
+                        }
                     }
-                    uint32_t hint = kNoInstance;
-                    if (a.hints && lit) hint = __ldg(a.hints + (size_t)hint_tile * (uint32_t)fc.num_lights + (uint32_t)light);
-                    float3 O = f3(0.0f, 0.0f, 0.0f), dir = O;
-                    float tMaxRay = 0.0f;
-                    if (lit) { // EvaluateShadow + TraceShadowRay (light.frag:137-146, :86-100)
-                        float3 C;
-                        shadow_ray_frame(L4, fragPos, N, camDist, O, C);
-                        const float3 T = rg_normalize(cross3(C, f3(0.0f, 1.0f, 0.0f)));
-                        const float3 B = rg_normalize(cross3(T, C));
-                        tMaxRay = rg_length(C);
-                        const float2 rng = blue_noise_sample(bn_r, bn_g, sample, fc.frame_mod);
-                        const float pointRadius = L4.radius * rg_sqrt(rng.x); // DiskSample (light.frag:57-61)
-                        float sn, cs;
+                    T = rg_normalize(cross3(C, f3(0.0f, 1.0f, 0.0f)));
+                    B = rg_normalize(cross3(T, C));
+                    tMinRay = 0.001f;
+                    tMaxRay = rg_length(C);
+                }
+                for (int i = 0; i < n_samples; i++) {
+                    const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
+                    float sn, cs;
+                    float3 dir;
+                    if (is_ao) { // HemisphereSample (light.frag:63-69)
+                        const float rr = rg_sqrt(rng.x);
+                        rg_sincos(6.283f * rng.y, &sn, &cs);
+                        dir = rg_combine(T, rr * cs, B, rr * sn, C, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
+                    } else { // DiskSample (light.frag:57-61)
+                        const float pointRadius = radius * rg_sqrt(rng.x);
                         rg_sincos(rng.y * 2.0f * kPI, &sn, &cs);
                         dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
                     }
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, lit);
-                    if (lit) {
-                        const int pos = q_count + __popc(m & lt_mask);
-                        const uint32_t kind = hint != kNoInstance ? kKindHinted : kKindRoot;
-                        const uint32_t meta = (uint32_t)lane | (kind << 5) | ((bit0 + (uint32_t)sample) << 8);
-                        ws.q0[pos] = make_float4(O.x, O.y, O.z, tMaxRay);
-                        ws.q1[pos] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(meta));
-                        ws.aux[pos] = hint;
-                    }
-                    q_count += __popc(m);
-                    sample++;
-                } else if (phase == 1) { // TraceAORays (light.frag:111-135): the per-pixel candidate lists
-                    const int n_samples = fc.ao_num_samples;
-                    if (n_samples <= 0) {
-                        phase = 3;
-                        continue;
-                    }
-                    int n_cand = -1; // < 0: the rays descend from the TLAS root
-                    if (lit && n_samples >= kMinCandSamples) {
-                        const float3 O = fragPos + N * (camDist * 0.01f);
-                        const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
-                        const float3 B = cross3(N, T);
-                        const float mreach = fabsf(fc.ao_max) * 1.001f;
-                        if (LUZ_AO_HEMISPHERE && fc.ao_min >= 0.0f && fc.ao_max >= 0.0f) {
-                            float3 lo, hi;
-                            hemisphere_box(O, T, B, N, mreach, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
-                            n_cand = collect_instances<false>(a.scene, lo, hi, ws.cand + lane, 32, kMaxCand, stack, nullptr);
-                            if (n_cand > 0) n_cand = filter_candidates<false>(a.scene, O, T, B, N, mreach, ws.cand + lane, 32, n_cand, nullptr);
-                        } else {
-                            const float3 ext = f3(mreach * sqrtf(T.x * T.x + B.x * B.x + N.x * N.x) + 1e-6f,
-                                                  mreach * sqrtf(T.y * T.y + B.y * B.y + N.y * N.y) + 1e-6f,
-                                                  mreach * sqrtf(T.z * T.z + B.z * B.z + N.z * N.z) + 1e-6f);
-                            n_cand = collect_instances<false>(a.scene, O - ext, O + ext, ws.cand + lane, 32, kMaxCand, stack, nullptr);
-                        }
-                    }
-                    ws.n_cand[lane] = n_cand;
-                    ao_active = lit && n_cand != 0; // an empty list: every AO ray of the pixel misses, no bit is set
-                    sample = 0;
-                    phase = __any_sync(0xFFFFFFFFu, ao_active) ? 2 : 3;
-                    __syncwarp();
-                } else { // phase 2: one AO sample of every pixel that has occluders within reach
-                    if (sample >= fc.ao_num_samples) {
-                        phase = 3;
-                        continue;
-                    }
-                    float3 O = f3(0.0f, 0.0f, 0.0f), dir = O;
-                    if (ao_active) { // HemisphereSample (light.frag:63-69); the frame is cheap to rebuild per round
-                        O = fragPos + N * (camDist * 0.01f);
-                        const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
-                        const float3 B = cross3(N, T);
-                        const float2 rng = blue_noise_sample(bn_r, bn_g, sample, fc.frame_mod);
-                        const float rr = rg_sqrt(rng.x);
-                        float sn, cs;
-                        rg_sincos(6.283f * rng.y, &sn, &cs);
-                        dir = rg_combine(T, rr * cs, B, rr * sn, N, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
-                    }
-                    const uint32_t m = __ballot_sync(0xFFFFFFFFu, ao_active);
-                    if (ao_active) {
-                        const int pos = q_count + __popc(m & lt_mask);
-                        const uint32_t kind = ws.n_cand[lane] > 0 ? kKindList : kKindRoot;
-                        const uint32_t meta = (uint32_t)lane | (kind << 5) | 0x80u | ((uint32_t)sample << 8);
-                        ws.q0[pos] = make_float4(O.x, O.y, O.z, fc.ao_max);
-                        ws.q1[pos] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(meta));
-                    }
-                    q_count += __popc(m);
-                    sample++;
-                }
-                __syncwarp();
-            }
-            if (q_count == 0) break; // nothing queued, nothing left to produce
-
-            // ---- drain one batch: the newest (most coherent) rays first ----
-            const int n = min(q_count, 32);
-            q_count -= n;
-            const bool valid = lane < n;
-            float4 i0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), i1 = i0;
-            uint32_t aux = 0;
-            if (valid) {
-                i0 = ws.q0[q_count + lane];
-                i1 = ws.q1[q_count + lane];
-                aux = ws.aux[q_count + lane];
-            }
-            __syncwarp(); // every item is in registers before the slots are reused
-            bool again = false;
-            const uint32_t meta = __float_as_uint(i1.w);
-            if (valid) {
-                const uint32_t owner = meta & 31u, kind = (meta >> 5) & 3u;
-                const bool is_ao = (meta & 0x80u) != 0u;
-                const uint32_t* cand = nullptr;
-                int stride = 0, n_cand = -1;
-                if (kind == kKindHinted) {
-                    cand = &aux; // a one-entry list in a register-backed local
-                    n_cand = 1;
-                } else if (kind == kKindList) {
-                    cand = ws.cand + owner;
-                    stride = 32;
-                    n_cand = ws.n_cand[owner];
-                }
-                const bool hit = trace_ray<false, false, false, ONE_VISIT>(a.scene, f3(i0.x, i0.y, i0.z), f3(i1.x, i1.y, i1.z),
-                                                                           is_ao ? fc.ao_min : 0.001f, i0.w, nullptr, nullptr, stack,
-                                                                           cand, stride, n_cand, false);
-                if (hit) {
-                    const uint32_t ox = bx * 8u + (owner & 7u), orow = by * 4u + (owner >> 3);
-                    const size_t opix = (size_t)band_row(fc, a.rows, band, orow) * fc.width + ox;
-                    const uint32_t bit = meta >> 8;
-                    uint32_t* word = is_ao ? a.ao_mask + opix * a.ao_words + (bit >> 5) : a.shadow_mask + opix * a.shadow_words + (bit >> 5);
-                    atomicOr(word, 1u << (bit & 31u));
-                } else if (kind == kKindHinted) {
-                    again = true; // the hinted instance does not occlude it: back into the queue as a root ray
+                    bits.push(trace_ray<false, false, false, ONE_VISIT>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, nullptr, stack, s_cand, 32,
+                                                                        n_cand, hinted));
                 }
             }
-            const uint32_t am = __ballot_sync(0xFFFFFFFFu, again);
-            if (am) {
-                if (again) {
-                    const int pos = q_count + __popc(am & lt_mask);
-                    ws.q0[pos] = i0;
-                    ws.q1[pos] = make_float4(i1.x, i1.y, i1.z, __uint_as_float(meta & ~(3u << 5)));
-                }
-                q_count += __popc(am);
-                __syncwarp();
-            }
+            bits.flush();
         }
+        __syncwarp();
     }
 }
 
@@ -774,7 +665,7 @@ __global__ void __launch_bounds__(128) k_light_shade(const LightArgs a) {
 } // namespace
 
 // The mask buffers (shadow_words / ao_words words per pixel) are part of the pass, not a debug option.
-cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done) {
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches) {
     if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
     const size_t px = (size_t)args.fc.width * args.fc.height;
     cudaError_t e;
@@ -783,7 +674,7 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
     // which ray kernel: the plain one (every ray of a pixel in one CTA) for the statistics variant and when forced by
     // LUZRT_RAY_KERNEL=plain; otherwise the specialised bodies (split when both kinds of ray exist)
-    static const int kernel_env = [] { // 0 auto (persistent warps + ray queue), 1 plain, 2 the per-pixel specialised kernels
+    static const int kernel_env = [] { // 0 auto (persistent warps, shadow rays as packets), 1 plain, 2 the per-pixel specialised kernels
         const char* e2 = getenv("LUZRT_RAY_KERNEL");
         return (e2 && e2[0] == 'p') ? 1 : (e2 && e2[0] == 's') ? 2 : 0;
     }();
@@ -793,21 +684,23 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     }();
     const bool any_shadow = args.fc.shadow_type == LUZW_SHADOW_RAYTRACING && args.fc.num_lights > 0;
     const bool any_ao = args.fc.ao_num_samples > 0;
+    // the packet kernel needs 8 stack entries per tree level in shared memory: very deep trees take the per-ray kernels
     const bool queue = !stats && kernel_env == 0 && (any_shadow || any_ao);
     const bool plain = !queue && (stats || kernel_env == 1 || (!any_shadow && !any_ao));
     const bool split = !queue && !plain && any_shadow && any_ao;
     const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands * (split ? 2u : 1u));
-    if (!queue) { // the queue kernel clears the mask words of the tiles it shades itself
+    if (!queue) { // the packet kernel clears the mask words of the tiles it shades itself
         if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
     }
     if (any_shadow && args.hints) { // one hint ray per tile and light
         const uint32_t n = grid.x * grid.y * args.rows.n_bands * (uint32_t)args.fc.num_lights;
         if (stats)
-            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, stream>>>(a2, args.hints, grid.x, grid.y);
+            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, stream>>>(a2, a2.hints, grid.x, grid.y);
         else
-            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, stream>>>(a2, args.hints, grid.x, grid.y);
+            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, stream>>>(a2, a2.hints, grid.x, grid.y);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++*launches;
     } else {
         a2.hints = nullptr;
     }
@@ -816,19 +709,52 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         return e2 ? atoi(e2) : 6;
     }();
     if (queue) {
-        static int blocks = 0;
-        if (!blocks) {
-            int dev = 0, sms = 0, per_sm = 0;
+        static const int pminb = [] { // resident CTAs per SM the persistent kernel is compiled for (LUZRT_PERSIST_MINB: tuning runs)
+            const char* e2 = getenv("LUZRT_PERSIST_MINB");
+            return e2 ? atoi(e2) : 6;
+        }();
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
             if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
             if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-            if ((e = cudaFuncSetAttribute(k_light_rays_queue<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(WarpQueue)))) != cudaSuccess) return e;
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_light_rays_queue<true>, 128, 4 * sizeof(WarpQueue))) != cudaSuccess) return e;
-            blocks = sms * max(per_sm, 1);
         }
         const uint32_t tx = (args.fc.width + 7) / 8, ty = (args.rows.rows + 3) / 4;
         const uint32_t n_tiles = tx * ty * args.rows.n_bands;
-        if ((e = cudaMemsetAsync(args.tile_counter, 0, sizeof(uint32_t), stream)) != cudaSuccess) return e;
-        k_light_rays_queue<true><<<min((uint32_t)blocks, (n_tiles + 3) / 4), 128, 4 * sizeof(WarpQueue), stream>>>(a2, args.tile_counter, tx, ty, n_tiles);
+        if ((e = cudaMemsetAsync(args.tile_counter, 0, 2 * sizeof(uint32_t), stream)) != cudaSuccess) return e;
+        // a kind of ray the frame does not have leaves its mask untouched: clear it here (the shading kernel does not read
+        // it, the debug read-back does)
+        if (!any_shadow && (e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
+        if (!any_ao && (e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
+        const size_t smem_p = 4 * sizeof(uint32_t) * kMaxCand * 32;
+        static const int merged_env = [] { // LUZRT_PERSIST_MERGED=1: both kinds of ray in one launch (A/B)
+            const char* e2 = getenv("LUZRT_PERSIST_MERGED");
+            return e2 && e2[0] == '1';
+        }();
+        auto launch = [&](auto kern, uint32_t* counter) -> cudaError_t {
+            int per_sm = 0;
+            cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem_p);
+            if (e3 != cudaSuccess) return e3;
+            kern<<<min((uint32_t)(sms * max(per_sm, 1)), (n_tiles + 3) / 4), 128, smem_p, stream>>>(a2, counter, tx, ty, n_tiles);
+            ++*launches;
+            return cudaGetLastError();
+        };
+        if (merged_env && any_shadow && any_ao) {
+            if ((e = launch(k_light_rays_persistent<true, 6, -1>, args.tile_counter)) != cudaSuccess) return e;
+        } else {
+            if (any_shadow) {
+                e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter)
+                               : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter)
+                                            : launch(k_light_rays_persistent<true, 6, 0>, args.tile_counter);
+                if (e != cudaSuccess) return e;
+            }
+            if (any_ao) {
+                e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 1>, args.tile_counter + 1)
+                               : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 1>, args.tile_counter + 1)
+                                            : launch(k_light_rays_persistent<true, 6, 1>, args.tile_counter + 1);
+                if (e != cudaSuccess) return e;
+            }
+        }
     } else if (split) {
         if (one_visit_env == 0)
             k_light_rays_split<false><<<grid, 128, smem, stream>>>(a2);
@@ -855,12 +781,14 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     else
         k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (!queue) ++*launches;
     if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;
     const dim3 sgrid((args.fc.width + 31) / 32, (args.rows.rows + 3) / 4, args.rows.n_bands);
     if (args.fc.shadow_type == LUZW_SHADOW_MAP)
         k_light_shade<true><<<sgrid, 128, 0, stream>>>(a2);
     else
         k_light_shade<false><<<sgrid, 128, 0, stream>>>(a2);
+    ++*launches;
     return cudaGetLastError();
 }
 

@@ -101,7 +101,7 @@ cudaError_t launch_volumetric_screen(cudaStream_t stream, const VolumetricArgs& 
 cudaError_t launch_volumetric_shadow_map(cudaStream_t stream, const VolumetricArgs& args);
 cudaError_t launch_shadow_map(cudaStream_t stream, const ShadowMapArgs& args);
 // ray kernel + shading kernel (light_pass.cu); the per-pixel visibility masks are cleared, written and read by it
-cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done);
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches);
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
 cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,
                                 const BandSet& rows);

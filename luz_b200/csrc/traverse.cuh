@@ -78,6 +78,9 @@ __device__ __forceinline__ TriData load_tri(const WideTri* tri) {
 __device__ __forceinline__ float edge_volume(const float3 d, const float3 m, const float4 M, const float4 E) {
     return fmaf(d.x, M.x, fmaf(d.y, M.y, fmaf(d.z, M.z, fmaf(m.x, E.x, fmaf(m.y, E.y, __fmul_rn(m.z, E.z))))));
 }
+// NEED_T == false (any-hit callers): only "tmin < t < tmax" is decided, by cross-multiplication with the sign of the
+// denominator instead of the IEEE division (a dozen instructions executed by the few lanes that sit in a leaf).
+template <bool NEED_T = true>
 __device__ __forceinline__ bool tri_test(const TriData& q, const float3 o, const float3 d, const float3 m, const float tmin,
                                          const float tmax, float& t_out, float& bu, float& bv) {
     const float U = edge_volume(d, m, q.mu, q.eu);
@@ -89,7 +92,12 @@ __device__ __forceinline__ bool tri_test(const TriData& q, const float3 o, const
     if (det == 0.0f) return false;
     // the plane: t = N . (p0 - o) / (N . d)
     const float3 N = f3(q.mv.w, q.ev.w, q.mw.w);
-    const float t = (q.eu.w - dot3_fma(N, o)) / dot3_fma(N, d);
+    const float num = q.eu.w - dot3_fma(N, o), den = dot3_fma(N, d);
+    if (!NEED_T) { // t = num / den lies in (tmin, tmax); den == 0 or NaN operands fail both forms
+        const float lo = __fmul_rn(tmin, den), hi = __fmul_rn(tmax, den);
+        return den > 0.0f ? (num > lo && num < hi) : (num < lo && num > hi);
+    }
+    const float t = num / den;
     if (!(t > tmin && t < tmax)) return false;
     t_out = t;
     bu = U / det;
@@ -473,7 +481,7 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                 if (STATS) st->tris++;
                 float t, bu, bv;
                 // the ray's moment is recomputed here rather than kept alive across the node loop (registers)
-                if (tri_test(q, o, d, cross3_rn(o, d), tmin, tmax, t, bu, bv)) {
+                if (tri_test<CLOSEST>(q, o, d, cross3_rn(o, d), tmin, tmax, t, bu, bv)) {
                     if (FACE_CULL) { // front faces (in the framebuffer of the emulated view) are not rasterised
                         const float3 n = f3(q.mv.w, q.ev.w, q.mw.w); // (p1 - p0) x (p2 - p0)
                         if (!(face_sign * dot3(d, n) > 0.0f)) continue;
