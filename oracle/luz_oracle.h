@@ -7,11 +7,18 @@
  * Vulkan driver supplies.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.  libluzrt.so never does.
  *
- * PARITY PINNING: the reference ships no tests, golden images or known-answer vectors for this
- * path and its GLSL cannot be executed in this environment (no Vulkan loader / glslang /
- * lavapipe), so the shader restatement is "parity unpinned" against reference *outputs*; it is
- * pinned only by hand-derived known answers (tests/test_oracle_kat.py) and by the reference's
- * own compiled host code for everything host-side (oracle/ref_dump.cpp -> tests/golden).
+ * PARITY PINNING: the reference ships no tests, golden images or known-answer vectors for this path and its Vulkan
+ * pipeline cannot run in this environment (no Vulkan loader / glslang / lavapipe).  The restatement is pinned to the
+ * reference's own code instead:
+ *   - shader side: oracle/glsl_harness/ rewrites the reference's light.frag / taa.comp / utils.glsl / LuzCommon.h
+ *     lexically for the host and compiles them against the reference's glm (oracle/_ref/libglsl_ref.so);
+ *     tests/test_glsl_pin.py runs that next to this oracle on identical inputs (every ray-query bit identical, radiance
+ *     and resolve equal to a few ulp; >= 70 % of the pixels bit-equal), and tests/golden/glsl_ref_*.npz keep its outputs
+ *     for machines without /root/reference;
+ *   - host side: the reference's own compiled loader / camera / struct layouts (oracle/ref_dump.cpp -> tests/golden);
+ *   - the fixed-function units the shaders call (texture unit, VK_KHR_ray_query, rasteriser) are driver territory with no
+ *     code in the reference tree: those are restated from the Vulkan rules the reference selects (sampler, cull mode,
+ *     ray flags) and checked by known answers (tests/test_oracle_kat.py).
  */
 #ifndef LUZ_ORACLE_H
 #define LUZ_ORACLE_H
