@@ -359,7 +359,9 @@ def run_ours(args):
         parity = BP.check_workload(wl, blue_noise(scenes), n_rows=args.parity_rows,
                                    candidate_rows=strips.owned_rows(rank, world, Hh) if world > 1 else None,
                                    taa=(world == 1))
-        parity["pass"] = bool(parity["agree"] >= BP.MASK_AGREE and parity["max_abs_mask_identical_pixels"] <= BP.RADIANCE_TOL
+        parity["pass"] = bool(parity["agree"] >= BP.MASK_AGREE
+                              and (parity["max_abs_mask_identical_pixels"] <= BP.RADIANCE_TOL or
+                                   parity["max_rel_mask_identical_pixels"] <= BP.REL_TOL)
                               and (parity["max_abs"] <= BP.RADIANCE_TOL or parity["psnr_db"] >= 50.0)
                               and parity.get("taa_max_abs", 0.0) <= BP.TAA_TOL
                               and parity.get("bvh2_check", {"rays_differ": 0})["rays_differ"] == 0)

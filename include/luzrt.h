@@ -88,7 +88,12 @@ enum {
     LUZRT_DEBUG_MASKS = 1, /* kept for ABI stability: the light pass always writes the per-ray visibility
                               bitmasks (they carry the rays' results to its shading kernel)            */
     LUZRT_DEBUG_STATS = 2, /* light pass counts nodes / triangles / instances per ray */
-    LUZRT_DEBUG_NO_HINTS = 4 /* shadow rays descend from the TLAS root without trying the tile's occluder hint first */
+    LUZRT_DEBUG_NO_HINTS = 4, /* shadow rays descend from the TLAS root without trying the tile's occluder hint first */
+    LUZRT_DEBUG_EXACT_MATH = 8 /* luzrt_light_pass / luzrt_taa_pass run the bit-faithful builds of the shading and resolve
+                                  kernels (every operation of light.frag / taa.comp in the shader's order, IEEE division
+                                  and square root, no FMA contraction) instead of the relaxed-precision ones a host gets
+                                  by default (MUFU reciprocals, contraction; ~1e-6 relative, inside the 1e-3 / 50 dB
+                                  tolerance).  Ray visibility is identical in both.                                  */
 };
 
 typedef struct luzrt_stats {

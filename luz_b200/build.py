@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v", "--expt-relaxed-constexpr",
     "-I", os.path.join(ROOT, "include"),
 ]
-CU_SOURCES = ["api.cu", "bvh_build.cu", "light_pass.cu", "taa.cu", "gbuffer.cu", "volumetric.cu", "shadow_map.cu"]
+CU_SOURCES = ["api.cu", "bvh_build.cu", "light_pass.cu", "taa.cu", "gbuffer.cu", "volumetric.cu", "shadow_map.cu", "relaxed.cu"]
 # The shading / resolve kernels restate GLSL that the oracle evaluates without FMA contraction; they are
 # built with -fmad=false so that implicit contraction cannot change results (ill-conditioned BRDF terms
 # amplify it), and use explicit fmaf() only where rounding is not part of parity (box tests).

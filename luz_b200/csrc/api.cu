@@ -151,6 +151,7 @@ struct luzrt_ctx {
     size_t shadow_mask_cap = 0, ao_mask_cap = 0;
     DeviceStats* d_stats = nullptr;
     unsigned long long* d_lit = nullptr;
+    float* d_pow22 = nullptr; // (c / 255)^2.2, c = 0..255 (light.frag:172), for the shading kernels
 
     cudaEvent_t ev[EV_COUNT][2]{};
     bool ev_valid[EV_COUNT]{};
@@ -352,9 +353,14 @@ int luzrt_create(int device_id, int rank, int world, luzrt_ctx** out) {
     for (int i = 0; i < EV_COUNT; i++)
         for (int k = 0; k < 2; k++) cudaEventCreate(&c->ev[i][k]);
     if (cudaMalloc(&c->d_stats, sizeof(DeviceStats)) != cudaSuccess ||
-        cudaMalloc(&c->d_lit, 64 * 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaMalloc(&c->d_lit, 64 * 16 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&c->d_pow22, 256 * sizeof(float)) != cudaSuccess) {
         luzrt_destroy(c);
         return LUZRT_E_NOMEM;
+    }
+    if (launch_pow22_table(c->stream, c->d_pow22) != cudaSuccess) {
+        luzrt_destroy(c);
+        return LUZRT_E_CUDA;
     }
     cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream);
     cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream);
@@ -392,7 +398,7 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints, c->d_pow22};
     for (float* p : c->shadow_data)
         if (p) cudaFree(p);
     for (void* p : ptrs)
@@ -1058,6 +1064,8 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     a.lit_counters = c->d_lit;
     a.tile_counter = reinterpret_cast<uint32_t*>(c->d_lit + 8); // a spare word of the counter block (only every 16th u64 counts)
     a.shadow_maps = c->d_shadow_recs;
+    a.pow22 = c->d_pow22;
+    a.exact_math = (c->debug & LUZRT_DEBUG_EXACT_MATH) ? 1u : 0u;
     a.hints = nullptr;
     static const bool hints_env = [] { // LUZRT_SHADOW_HINTS=0: no occluder hints (tuning / A-B runs)
         const char* e = getenv("LUZRT_SHADOW_HINTS");
@@ -1255,7 +1263,7 @@ int luzrt_taa_pass(luzrt_ctx* c, int reconstruct) {
     CU(c, wait_gather(c, a.light_in, a.history, a.out));
     CU(c, wait_download(c, a.out));
     ev_begin(c, EV_TAA);
-    CU(c, launch_taa_pass(c->stream, a));
+    CU(c, launch_taa_pass(c->stream, a, (c->debug & LUZRT_DEBUG_EXACT_MATH) != 0));
     c->launches++;
     ev_end(c, EV_TAA);
     std::swap(c->lightA, c->lightB); // DeferredRenderer.cpp:443

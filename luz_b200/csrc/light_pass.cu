@@ -25,6 +25,7 @@
 #include <cstdlib>
 
 #include "passes.h"
+#include "shade_kernel.cuh"
 #include "traverse.cuh"
 
 namespace luz {
@@ -47,23 +48,6 @@ __device__ __forceinline__ float2 blue_noise_sample(float bn_r, float bn_g, int 
     const float k = (float)(128 * i + frame_mod);
     const float off = __fmul_rn(kGoldenRatio, k);
     return make_float2(fractf(__fadd_rn(bn_r, off)), fractf(__fadd_rn(bn_g, off)));
-}
-
-// light.frag:17-26
-__device__ __forceinline__ float distribution_ggx(float3 N, float3 H, float roughness) {
-    const float a = roughness * roughness;
-    const float a2 = a * a;
-    const float NdotH = fmaxf(dot3(N, H), 0.0f);
-    const float NdotH2 = NdotH * NdotH;
-    float denom = (NdotH2 * (a2 - 1.0f) + 1.0f);
-    denom = kPI * denom * denom;
-    return a2 / denom;
-}
-// light.frag:28-36
-__device__ __forceinline__ float geometry_schlick_ggx(float NdotV, float roughness) {
-    const float r = roughness + 1.0f;
-    const float k = (r * r) / 8.0f;
-    return NdotV / (NdotV * (1.0f - k) + k);
 }
 
 // ---- ray generation arithmetic ---------------------------------------------------------------------------------
@@ -105,20 +89,6 @@ __device__ __forceinline__ float3 rg_combine(float3 a, float x, float3 b, float 
     return a * x + b * y + c * z;
 }
 #endif
-
-// number of set bits among bits [b0, b0 + n) of a pixel's mask words
-__device__ __forceinline__ uint32_t count_bits(const uint32_t* __restrict__ m, uint32_t b0, int n) {
-    uint32_t c = 0;
-    while (n > 0) {
-        const uint32_t w = __ldg(m + (b0 >> 5)), s = b0 & 31u;
-        const uint32_t take = min((uint32_t)n, 32u - s);
-        const uint32_t sel = take == 32u ? 0xFFFFFFFFu : ((1u << take) - 1u);
-        c += __popc((w >> s) & sel);
-        b0 += take;
-        n -= (int)take;
-    }
-    return c;
-}
 
 // Appends one visibility bit to a pixel's mask; words are stored when they fill up (and by flush()).
 struct BitWriter {
@@ -544,125 +514,14 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const
     }
 }
 
-// ---- kernel 2: shading -----------------------------------------------------------------------------------------
-// SMAP: compiled with the shadow-map branch of EvaluateShadow (light.frag:147-165).
-template <bool SMAP>
-__global__ void __launch_bounds__(128) k_light_shade(const LightArgs a) {
-    __shared__ LightRec s_lights[kLightChunk];
-    const FrameConst& fc = a.fc;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t x = blockIdx.x * 32 + lane;
-    const uint32_t r = blockIdx.y * 4 + warp;
-    const bool in_image = x < fc.width && r < a.rows.rows;
-    const uint32_t y = in_image ? band_row(fc, a.rows, blockIdx.z, r) : 0u;
-    const size_t pix = (size_t)y * fc.width + x;                   // G-buffer, masks: natural row order
-    const size_t opix = (size_t)storage_row(fc, y) * fc.width + x; // light image: banded storage order
-
-    // ---- G-buffer fetch (light.frag:172-176; texel loads) ----
-    float3 N = f3(0.0f, 0.0f, 0.0f);
-    uchar4 a8 = make_uchar4(0, 0, 0, 0), m8 = a8, e8 = a8;
-    float depth = 1.0f;
-    if (in_image) {
-        const float4 n4 = __ldg(a.normal + pix);
-        N = f3(n4.x, n4.y, n4.z);
-        a8 = __ldg(a.albedo + pix);
-        m8 = __ldg(a.material + pix);
-        e8 = __ldg(a.emission + pix);
-        depth = __ldg(a.depth + pix);
-    }
-    const float3 ambientLight = f3(fc.ambient[0], fc.ambient[1], fc.ambient[2]);
-    const bool lit = in_image && (length3(N) != 0.0f); // :178
-    if (in_image && !lit) a.out[opix] = make_float4(ambientLight.x, ambientLight.y, ambientLight.z, 1.0f);
-    { // lit pixels of the rows this rank owns (halo rows are recomputation): the frame's ray count follows from it,
-      // whichever ray kernels ran (shadow rays only, AO rays only, both, none)
-        const bool counted = r >= a.count_row_begin && r < a.count_row_end;
-        const unsigned int lit_warp = __popc(__ballot_sync(0xFFFFFFFFu, lit && counted));
-        if (lane == 0 && lit_warp)
-            atomicAdd(a.lit_counters + 16 * ((blockIdx.x + (blockIdx.y * 4u + warp + blockIdx.z * 7u) * 29u) & 63u),
-                      (unsigned long long)lit_warp);
-    }
-
-    const float3 albedo = f3(powf((float)a8.x / 255.0f, 2.2f), powf((float)a8.y / 255.0f, 2.2f),
-                             powf((float)a8.z / 255.0f, 2.2f));
-    const float roughness = (float)m8.x / 255.0f, metallic = (float)m8.y / 255.0f, occlusion = (float)m8.z / 255.0f;
-    const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
-    const float3 fragPos = depth_to_world(fc, u, v, depth);
-    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
-    const float3 V = normalize3(camPos - fragPos);
-    const float3 F0 = f3(0.04f, 0.04f, 0.04f) * (1.0f - metallic) + albedo * metallic;
-    const float camDist = length3(fragPos - camPos);
-    const float NdotV = fmaxf(dot3(N, V), 0.0f);
-    const float ggxV = geometry_schlick_ggx(NdotV, roughness);
-    const uint32_t* smask = a.shadow_mask + pix * a.shadow_words;
-    const uint32_t* amask = a.ao_mask + pix * a.ao_words;
-
-    float3 Lo = f3(0.0f, 0.0f, 0.0f);
-    uint32_t shadow_bit = 0;
-    for (int base = 0; base < fc.num_lights; base += kLightChunk) {
-        const int chunk = min(kLightChunk, fc.num_lights - base);
-        __syncthreads();
-        for (int k = threadIdx.x; k < chunk * 4; k += blockDim.x)
-            reinterpret_cast<float4*>(s_lights)[k] = __ldg(reinterpret_cast<const float4*>(a.lights + base) + k);
-        __syncthreads();
-        if (!lit) continue;
-        for (int li = 0; li < chunk; li++) {
-            const LightRec L4 = s_lights[li];
-            const float3 lpos = f3(L4.position_inner.x, L4.position_inner.y, L4.position_inner.z);
-            const float3 ldir = f3(L4.direction_outer.x, L4.direction_outer.y, L4.direction_outer.z);
-            const float3 Lvec = lpos - fragPos;
-            const float dist = length3(Lvec);
-            float3 L = Lvec / dist; // normalize(L_)
-            float attenuation = 1.0f;
-            if (L4.type == LUZW_LIGHT_DIRECTIONAL) {
-                L = normalize3(-ldir);
-            } else if (L4.type == LUZW_LIGHT_SPOT) {
-                attenuation = 1.0f / (dist * dist);
-                const float theta = dot3(L, normalize3(-ldir));
-                const float epsilon = L4.position_inner.w - L4.direction_outer.w;
-                attenuation *= clampf((theta - L4.direction_outer.w) / epsilon, 0.0f, 1.0f);
-            } else if (L4.type == LUZW_LIGHT_POINT) {
-                attenuation = 1.0f / (dist * dist);
-            }
-            // shadow factor: RT with samples -> occluded fraction; RT with 0 samples -> 0; otherwise 1 (:166-168)
-            const int n_samples = fc.shadow_type == LUZW_SHADOW_RAYTRACING ? L4.num_shadow_samples : 0;
-            float shadowFactor = fc.shadow_type != LUZW_SHADOW_RAYTRACING ? 1.0f : 0.0f;
-            if (n_samples > 0) {
-                shadowFactor = (float)count_bits(smask, shadow_bit, n_samples) / (float)n_samples;
-                shadow_bit += (uint32_t)n_samples;
-            }
-            if (SMAP && fc.shadow_type == LUZW_SHADOW_MAP && L4.shadow_map != -1) { // light.frag:147-165
-                const float3 O = fragPos + N * fmaxf(camDist * 0.01f, 0.05f);
-                shadowFactor = shadow_map_factor(a.shadow_maps[base + li], L4.type, lpos, fragPos, O);
-            }
-            const float3 lcol = f3(L4.color_intensity.x, L4.color_intensity.y, L4.color_intensity.z);
-            const float3 radiance = lcol * L4.color_intensity.w * attenuation * (1.0f - shadowFactor);
-
-            const float3 H = normalize3(V + L);
-            const float NDF = distribution_ggx(N, H, roughness);
-            const float NdotL = fmaxf(dot3(N, L), 0.0f);
-            const float G = geometry_schlick_ggx(NdotL, roughness) * ggxV; // GeometrySmith :38-45
-            const float fp = powf(clampf(1.0f - clampf(dot3(H, V), 0.0f, 1.0f), 0.0f, 1.0f), 5.0f);
-            const float3 F = F0 + (f3(1.0f, 1.0f, 1.0f) - F0) * fp; // FresnelSchlick :47-49
-            const float3 num = NDF * G * F;
-            const float denom = 4.0f * NdotV * NdotL + 0.0001f;
-            const float3 spec = num / denom;
-            float3 kD = f3(1.0f, 1.0f, 1.0f) - F;
-            kD = kD * (1.0f - metallic);
-            Lo = Lo + (kD * albedo / kPI + spec) * radiance * NdotL;
-        }
-    }
-    if (lit) {
-        float rayTracedAo = 1.0f;
-        const int n_ao = fc.ao_num_samples;
-        if (n_ao != 0) rayTracedAo = ((float)n_ao - (float)count_bits(amask, 0u, n_ao)) / (float)n_ao; // ao / aoNumSamples
-        const float3 emission = f3((float)e8.x / 255.0f, (float)e8.y / 255.0f, (float)e8.z / 255.0f);
-        const float3 ambient = ambientLight * albedo * occlusion * rayTracedAo;
-        const float3 color = ambient + Lo + emission;
-        a.out[opix] = make_float4(color.x, color.y, color.z, 1.0f);
-    }
-}
+__global__ void k_pow22_table(float* __restrict__ t) { t[threadIdx.x] = powf((float)threadIdx.x / 255.0f, 2.2f); } // light.frag:172
 
 } // namespace
+
+cudaError_t launch_pow22_table(cudaStream_t stream, float* table256) {
+    k_pow22_table<<<1, 256, 0, stream>>>(table256);
+    return cudaGetLastError();
+}
 
 // The mask buffers (shadow_words / ao_words words per pixel) are part of the pass, not a debug option.
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches) {
@@ -783,12 +642,13 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (!queue) ++*launches;
     if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;
+    ++*launches;
+    if (!args.exact_math) return launch_light_shade_relaxed(stream, a2);
     const dim3 sgrid((args.fc.width + 31) / 32, (args.rows.rows + 3) / 4, args.rows.n_bands);
     if (args.fc.shadow_type == LUZW_SHADOW_MAP)
-        k_light_shade<true><<<sgrid, 128, 0, stream>>>(a2);
+        k_light_shade<true, false><<<sgrid, 128, 0, stream>>>(a2);
     else
-        k_light_shade<false><<<sgrid, 128, 0, stream>>>(a2);
-    ++*launches;
+        k_light_shade<false, false><<<sgrid, 128, 0, stream>>>(a2);
     return cudaGetLastError();
 }
 

@@ -31,6 +31,8 @@ struct LightArgs {
     uint32_t* hints;                         // occluder hints [tile][light] of the shadow rays (nullptr: none), light_pass.cu
     uint32_t* tile_counter;                  // work counter of the persistent ray kernel (reset per launch)
     const ShadowMapRec* shadow_maps;         // per light, scene order (read only when fc.shadow_type == LUZW_SHADOW_MAP)
+    const float* pow22;                      // 256 floats: (c / 255)^2.2 (launch_pow22_table)
+    uint32_t exact_math;                     // 1: the bit-faithful shading kernel (LUZRT_DEBUG_EXACT_MATH)
 };
 
 struct TaaArgs {
@@ -102,7 +104,12 @@ cudaError_t launch_volumetric_shadow_map(cudaStream_t stream, const VolumetricAr
 cudaError_t launch_shadow_map(cudaStream_t stream, const ShadowMapArgs& args);
 // ray kernel + shading kernel (light_pass.cu); the per-pixel visibility masks are cleared, written and read by it
 cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches);
-cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args);
+// exact: the bit-faithful build (LUZRT_DEBUG_EXACT_MATH) instead of the relaxed-precision one (relaxed.cu)
+cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args, bool exact);
+cudaError_t launch_taa_relaxed(cudaStream_t stream, const TaaArgs& args);
+cudaError_t launch_light_shade_relaxed(cudaStream_t stream, const LightArgs& args);
+// fills the 256-entry table (c / 255)^2.2 the shading kernels look albedo up in
+cudaError_t launch_pow22_table(cudaStream_t stream, float* table256);
 cudaError_t launch_compose_pass(cudaStream_t stream, const FrameConst& fc, const float4* light_in, uchar4* out_bgra,
                                 const BandSet& rows);
 // copies rows between the banded storage order of the light images and the natural row order

@@ -33,18 +33,29 @@ def check_radiance(got, ref, what):
 
 
 def run_light(rt, sc, gb, frame, bn, extra=None):
+    """Returns the image of the BIT-FAITHFUL shading build (what the oracle is compared with value by value), the masks
+    and the statistics; on the way asserts that every variant a host can get agrees with it."""
     rt.set_scene(sc["scene"], extra)
     rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
-    rt.set_debug(R.DEBUG_MASKS | R.DEBUG_STATS)
+    rt.set_debug(R.DEBUG_MASKS | R.DEBUG_STATS | R.DEBUG_EXACT_MATH)
     rt.light_pass(frame)
     out = rt.read(R.IMG_LIGHT)
     sm, am, st = rt.read(R.SHADOW_MASK), rt.read(R.AO_MASK), rt.read(R.STATS)
-    # the pass above ran the statistics variant of the ray kernel; the kernels a host gets without LUZRT_DEBUG_STATS
-    # (specialised shadow / AO bodies, light_pass.cu) must produce the same bits and the same image
-    rt.set_debug(0)
+    # the pass above ran the statistics variant of the ray kernel; the ray kernels a host gets without LUZRT_DEBUG_STATS
+    # (persistent warps, one specialised launch per kind of ray, light_pass.cu) must produce the same bits and image
+    rt.set_debug(R.DEBUG_EXACT_MATH)
     rt.light_pass(frame)
     assert np.array_equal(rt.read(R.SHADOW_MASK), sm) and np.array_equal(rt.read(R.AO_MASK), am)
     assert np.array_equal(rt.read(R.IMG_LIGHT), out, equal_nan=True)
+    # and the relaxed-precision shading build (the default): same bits, image inside the contract's tolerance
+    rt.set_debug(0)
+    rt.light_pass(frame)
+    assert np.array_equal(rt.read(R.SHADOW_MASK), sm) and np.array_equal(rt.read(R.AO_MASK), am)
+    relaxed = rt.read(R.IMG_LIGHT)
+    assert np.array_equal(np.isnan(relaxed), np.isnan(out))
+    fin = np.isfinite(out).all(axis=-1) & np.isfinite(relaxed).all(axis=-1)
+    if fin.any():
+        check_radiance(relaxed[fin], out[fin], "relaxed shading build vs bit-faithful build")
     return out, sm, am, st
 
 
@@ -186,6 +197,14 @@ def test_taa_parity(rt_factory):
         rt.set_gbuffer(gb.albedo, gb.normal, gb.material, gb.emission, gb.depth)
         rt.set_scene(sc["scene"])
         rt.set_debug(0)
+        rt.light_pass(11)
+        light0 = rt.read(R.IMG_LIGHT)
+        rt.taa_pass(reconstruct)  # the relaxed-precision resolve (the default build): inside the contract's tolerance
+        res0r = rt.read(R.IMG_LIGHT)
+        ref0 = O.taa_pass(sc["scene"], light0, light0, gb.depth, reconstruct)
+        check_radiance(res0r, ref0, "relaxed TAA build")
+        assert float(np.abs(res0r - ref0).max()) <= 1e-3
+        rt.set_debug(R.DEBUG_EXACT_MATH)  # from here on: the bit-faithful builds against the oracle at 1e-4
         rt.light_pass(11)
         light0 = rt.read(R.IMG_LIGHT)
         rt.taa_pass(reconstruct)
