@@ -160,6 +160,8 @@ struct luzrt_ctx {
     // the frame gather runs on its own stream so that it overlaps the next frame's light pass; whoever touches
     // the buffer being gathered waits for ev_gathered first (wait_gather)
     cudaStream_t comm_stream = nullptr;
+    cudaStream_t aux_stream = nullptr; // light pass: hint pass + shadow-ray launch (the AO-ray launch runs on `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_resolved = nullptr, ev_gathered = nullptr;
     const void* gather_buf = nullptr; // image with a gather in flight (nullptr: none)
     uint32_t min_node_lanes = 33; // > 32: one node visit per pass of the traversal loop (fastest on C2-C4; LUZRT_MIN_NODE_LANES)
@@ -375,6 +377,12 @@ void luzrt_destroy(luzrt_ctx* c) {
     DeviceGuard g(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->aux_stream) {
+        cudaStreamSynchronize(c->aux_stream);
+        cudaStreamDestroy(c->aux_stream);
+        cudaEventDestroy(c->ev_fork);
+        cudaEventDestroy(c->ev_join);
+    }
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (cudaStream_t st : {c->upload_stream, c->download_stream})
         if (st) {
@@ -1085,7 +1093,12 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
     CU(c, cudaMemsetAsync(c->d_lit, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     if (stats) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
     CU(c, cudaEventRecord(c->ev[EV_LIGHT_RAYS][0], c->stream));
-    CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1], &c->launches));
+    if (!c->aux_stream) { // second stream of the light pass (hint pass + shadow rays next to the AO rays)
+        CU(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1], &c->launches, c->aux_stream, c->ev_fork, c->ev_join));
     c->ev_valid[EV_LIGHT_RAYS] = true;
     ev_end(c, EV_LIGHT);
     return LUZRT_OK;

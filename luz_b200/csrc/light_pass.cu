@@ -2,13 +2,14 @@
 // per ray (1 = occluded) in the per-pixel visibility masks (all ray state in registers, no ray buffers in HBM);
 // k_light_shade evaluates light.frag:171-235 with the occluded fractions read back from those bits.
 //
-//   k_shadow_hints        one ray per 16x8 tile and light: an occluding instance the tile's shadow rays try first
-//   k_light_rays_split    two CTAs per tile: part 0 the shadow rays, part 1 the AO rays (frames that have both)
-//   k_light_rays_part<P>  frames with one kind of ray (C4: shadow rays only; shadowType == ShadowMap: AO rays only)
-//   k_light_rays          every ray of a pixel in one CTA: the LUZRT_DEBUG_STATS variant (counts nodes / triangles /
-//                         instances) and the A/B baseline
-//   k_light_shade         Cook-Torrance over the lights, shadow factors and AO from the masks
-// All ray kernels instantiate one body (light_rays_body) and produce identical bits (tests/test_gpu_parity.py run_light).
+//   k_shadow_hints           one ray per 16x8 tile and light: an occluding instance the tile's shadow rays try first
+//   k_light_rays_persistent  the ray kernels a host gets: persistent warps pull 8x4-pixel tiles from an atomic counter;
+//                            one specialised launch per kind of ray (PART 0 shadow rays, PART 1 AO rays), the AO launch
+//                            overlapping the hint pass and filling the tail of the shadow launch
+//   k_light_rays             every ray of a pixel in one CTA: the LUZRT_DEBUG_STATS variant (counts nodes / triangles /
+//                            instances) and the reference the persistent kernels are tested against bit for bit
+//   k_light_shade            (shade_kernel.cuh) Cook-Torrance over the lights, shadow factors and AO from the masks
+// All ray kernels produce identical bits (tests/test_gpu_parity.py run_light).
 //
 // Why rays and shading are separate kernels: a single fused kernel (this file up to commit "Host path: read-back in flight ...") keeps the whole
 // BRDF state of the pixel alive inside the traversal loop (albedo, F0, V, Lo, roughness ... ~30 registers) next to
@@ -182,8 +183,7 @@ __global__ void __launch_bounds__(128) k_shadow_hints(const LightArgs a, uint32_
     }
 }
 
-// PART -1: every ray of the pixel; 0: its shadow rays only; 1: its AO rays only (they write different mask arrays).
-template <bool STATS, int PART, bool ONE_VISIT>
+template <bool STATS>
 __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32_t band) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LightRec* s_lights = reinterpret_cast<LightRec*>(smem_raw);
@@ -235,7 +235,6 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
         if (!lit) continue;
         for (int li = 0; li < chunk; li++) {
             const bool is_ao = base + li == fc.num_lights;
-            if (PART == (is_ao ? 0 : 1)) continue; // the other CTA's rays
             float3 O, T, B, C; // ray origin and sampling frame
             float radius = 0.0f, tMinRay, tMaxRay;
             int n_samples;
@@ -316,7 +315,7 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
                 }
                 n_rays += counted;
                 LocalStats rst = {0, 0, 0};
-                const bool hit = trace_ray<false, STATS, false, ONE_VISIT>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, STATS ? &rst : &st, stack, s_cand, 128, n_cand, hinted);
+                const bool hit = trace_ray<false, STATS, false, false>(a.scene, O, dir, tMinRay, tMaxRay, nullptr, STATS ? &rst : &st, stack, s_cand, 128, n_cand, hinted);
                 if (STATS) {
                     st.nodes += rst.nodes, st.tris += rst.tris, st.insts += rst.insts;
                     if (counted) {
@@ -362,29 +361,15 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
 
 template <bool STATS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays(const LightArgs a) {
-    light_rays_body<STATS, -1, false>(a, blockIdx.z);
+    light_rays_body<STATS>(a, blockIdx.z);
 }
 
-// Frames with one kind of ray only (PART 0: shadow rays, e.g. C4; PART 1: AO rays, e.g. shadowType == ShadowMap).
-template <int PART, bool ONE_VISIT>
-__global__ void __launch_bounds__(128, 6) k_light_rays_part(const LightArgs a) {
-    light_rays_body<false, PART, ONE_VISIT>(a, blockIdx.z);
-}
-
-// Both kinds: two CTAs per tile, blockIdx.z = part * n_bands + band, part 0 fires the shadow rays, part 1 the AO rays
-// (they write different mask arrays).  The bodies are specialised at compile time (the shadow body holds no candidate
-// list code, the AO body no light loop), which is worth 2-3 % on a whole 4K frame, and halving the work of a CTA
-// halves the tail of the launch, which is what a rank of a multi-GPU frame (1/8 of the pixels, ~10 waves of CTAs whose
-// cost varies from nothing for sky to ~300 us) loses most of its time to (profiles/r1_ab_ray_parts.md).
-template <bool ONE_VISIT>
-__global__ void __launch_bounds__(128, 6) k_light_rays_split(const LightArgs a) {
-    if (blockIdx.z < a.rows.n_bands)
-        light_rays_body<false, 0, ONE_VISIT>(a, blockIdx.z);
-    else
-        light_rays_body<false, 1, ONE_VISIT>(a, blockIdx.z - a.rows.n_bands);
-}
-
-// ---- persistent warps, every ray per lane (the body above inside a tile loop) -----------------------------------------
+// ---- the ray kernels a host gets: persistent warps ---------------------------------------------------------------------
+// The same per-lane ray loop as above inside a tile loop: a warp pulls 8x4-pixel tiles from an atomic counter until none
+// is left (a launch has no tail of half-empty waves, whatever share of the frame a rank owns) and clears the mask words of
+// its tile itself (no memset pass over the frame).  Lights are read through the read-only cache at a warp-uniform address
+// (no staging, no barriers).  What was tried on top of this and lost is recorded in profiles/r2_ray_queue_experiment.md:
+// ballot-compacted ray queues, shadow rays as warp packets with one shared stack, both kinds of ray in one body.
 // PART 0: the shadow rays, 1: the AO rays (two launches, each body specialised at compile time); -1: both in one launch.
 template <bool ONE_VISIT, int MIN_BLOCKS, int PART>
 __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const LightArgs a, uint32_t* __restrict__ tile_counter,
@@ -524,53 +509,40 @@ cudaError_t launch_pow22_table(cudaStream_t stream, float* table256) {
 }
 
 // The mask buffers (shadow_words / ao_words words per pixel) are part of the pass, not a debug option.
-cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches) {
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches,
+                              cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     if (args.rows.rows == 0 || args.rows.n_bands == 0 || args.fc.width == 0) return cudaSuccess;
     const size_t px = (size_t)args.fc.width * args.fc.height;
     cudaError_t e;
     LightArgs a2 = args;
     a2.cand_offset = (uint32_t)(sizeof(LightRec) * (size_t)max(1, min(args.fc.num_lights, kLightChunk)));
     const size_t smem = a2.cand_offset + sizeof(uint32_t) * kMaxCand * 128;
-    // which ray kernel: the plain one (every ray of a pixel in one CTA) for the statistics variant and when forced by
-    // LUZRT_RAY_KERNEL=plain; otherwise the specialised bodies (split when both kinds of ray exist)
-    static const int kernel_env = [] { // 0 auto (persistent warps, shadow rays as packets), 1 plain, 2 the per-pixel specialised kernels
+    static const int kernel_env = [] { // LUZRT_RAY_KERNEL=plain: the per-pixel kernel without statistics (A/B runs)
         const char* e2 = getenv("LUZRT_RAY_KERNEL");
-        return (e2 && e2[0] == 'p') ? 1 : (e2 && e2[0] == 's') ? 2 : 0;
-    }();
-    static const int one_visit_env = [] { // 0: the yielding node loop in the specialised kernels (tuning runs; the `if` form is 2-3 % faster there)
-        const char* e2 = getenv("LUZRT_ONE_VISIT");
-        return e2 ? atoi(e2) : -1;
+        return (e2 && e2[0] == 'p') ? 1 : 0;
     }();
     const bool any_shadow = args.fc.shadow_type == LUZW_SHADOW_RAYTRACING && args.fc.num_lights > 0;
     const bool any_ao = args.fc.ao_num_samples > 0;
-    // the packet kernel needs 8 stack entries per tree level in shared memory: very deep trees take the per-ray kernels
-    const bool queue = !stats && kernel_env == 0 && (any_shadow || any_ao);
-    const bool plain = !queue && (stats || kernel_env == 1 || (!any_shadow && !any_ao));
-    const bool split = !queue && !plain && any_shadow && any_ao;
-    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands * (split ? 2u : 1u));
-    if (!queue) { // the packet kernel clears the mask words of the tiles it shades itself
-        if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
-    }
-    if (any_shadow && args.hints) { // one hint ray per tile and light
+    const bool persistent = !stats && kernel_env == 0 && (any_shadow || any_ao);
+    const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands); // 16x8 tiles: hints, plain kernel
+    if (!(any_shadow && args.hints)) a2.hints = nullptr;
+    auto launch_hints = [&](cudaStream_t st) -> cudaError_t { // one hint ray per tile and light
         const uint32_t n = grid.x * grid.y * args.rows.n_bands * (uint32_t)args.fc.num_lights;
         if (stats)
-            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, stream>>>(a2, a2.hints, grid.x, grid.y);
+            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, grid.x, grid.y);
         else
-            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, stream>>>(a2, a2.hints, grid.x, grid.y);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, grid.x, grid.y);
         ++*launches;
-    } else {
-        a2.hints = nullptr;
-    }
-    static const int minb = [] { // resident CTAs per SM the plain ray kernel is compiled for (LUZRT_LIGHT_MINB: tuning runs)
-        const char* e2 = getenv("LUZRT_LIGHT_MINB");
-        return e2 ? atoi(e2) : 6;
-    }();
-    if (queue) {
-        static const int pminb = [] { // resident CTAs per SM the persistent kernel is compiled for (LUZRT_PERSIST_MINB: tuning runs)
+        return cudaGetLastError();
+    };
+    if (persistent) {
+        static const int pminb = [] { // resident CTAs per SM the persistent kernels are compiled for (LUZRT_PERSIST_MINB: tuning runs)
             const char* e2 = getenv("LUZRT_PERSIST_MINB");
             return e2 ? atoi(e2) : 6;
+        }();
+        static const bool overlap_env = [] { // LUZRT_RAY_OVERLAP=0: hints, shadow rays, AO rays strictly one after the other
+            const char* e2 = getenv("LUZRT_RAY_OVERLAP");
+            return !(e2 && e2[0] == '0');
         }();
         static int sms = 0;
         if (!sms) {
@@ -586,61 +558,53 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         if (!any_shadow && (e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
         if (!any_ao && (e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
         const size_t smem_p = 4 * sizeof(uint32_t) * kMaxCand * 32;
-        static const int merged_env = [] { // LUZRT_PERSIST_MERGED=1: both kinds of ray in one launch (A/B)
-            const char* e2 = getenv("LUZRT_PERSIST_MERGED");
-            return e2 && e2[0] == '1';
-        }();
-        auto launch = [&](auto kern, uint32_t* counter) -> cudaError_t {
+        auto launch = [&](auto kern, uint32_t* counter, cudaStream_t st) -> cudaError_t {
             int per_sm = 0;
             cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem_p);
             if (e3 != cudaSuccess) return e3;
-            kern<<<min((uint32_t)(sms * max(per_sm, 1)), (n_tiles + 3) / 4), 128, smem_p, stream>>>(a2, counter, tx, ty, n_tiles);
+            kern<<<min((uint32_t)(sms * max(per_sm, 1)), (n_tiles + 3) / 4), 128, smem_p, st>>>(a2, counter, tx, ty, n_tiles);
             ++*launches;
             return cudaGetLastError();
         };
-        if (merged_env && any_shadow && any_ao) {
-            if ((e = launch(k_light_rays_persistent<true, 6, -1>, args.tile_counter)) != cudaSuccess) return e;
-        } else {
-            if (any_shadow) {
-                e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter)
-                               : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter)
-                                            : launch(k_light_rays_persistent<true, 6, 0>, args.tile_counter);
-                if (e != cudaSuccess) return e;
-            }
-            if (any_ao) {
-                e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 1>, args.tile_counter + 1)
-                               : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 1>, args.tile_counter + 1)
-                                            : launch(k_light_rays_persistent<true, 6, 1>, args.tile_counter + 1);
-                if (e != cudaSuccess) return e;
-            }
+        // The AO launch needs no hints: it goes first on the pass's stream while the hint pass (a few latency-bound warps)
+        // and then the shadow launch run on a second stream -- the hint pass hides behind AO work, and the CTAs of the
+        // shadow launch move in as the persistent AO CTAs run out of tiles (and the other way round at its end).
+        const bool fork = overlap_env && any_shadow && any_ao && aux && ev_fork && ev_join;
+        cudaStream_t shadow_stream = fork ? aux : stream;
+        if (fork) {
+            if ((e = cudaEventRecord(ev_fork, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(aux, ev_fork, 0)) != cudaSuccess) return e;
         }
-    } else if (split) {
-        if (one_visit_env == 0)
-            k_light_rays_split<false><<<grid, 128, smem, stream>>>(a2);
+        if (any_shadow) {
+            if (a2.hints && (e = launch_hints(shadow_stream)) != cudaSuccess) return e;
+            e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter, shadow_stream)
+                           : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter, shadow_stream)
+                                        : launch(k_light_rays_persistent<true, 6, 0>, args.tile_counter, shadow_stream);
+            if (e != cudaSuccess) return e;
+        }
+        if (any_ao) {
+            e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 1>, args.tile_counter + 1, stream)
+                           : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 1>, args.tile_counter + 1, stream)
+                                        : launch(k_light_rays_persistent<true, 6, 1>, args.tile_counter + 1, stream);
+            if (e != cudaSuccess) return e;
+        }
+        if (fork) {
+            if ((e = cudaEventRecord(ev_join, aux)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(stream, ev_join, 0)) != cudaSuccess) return e;
+        }
+    } else {
+        // the per-pixel kernel: statistics variant, LUZRT_RAY_KERNEL=plain, and frames without rays (it then only exists
+        // to leave cleared masks behind)
+        if ((e = cudaMemsetAsync(args.shadow_mask, 0, px * args.shadow_words * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(args.ao_mask, 0, px * args.ao_words * 4, stream)) != cudaSuccess) return e;
+        if (a2.hints && (e = launch_hints(stream)) != cudaSuccess) return e;
+        if (stats)
+            k_light_rays<true, 4><<<grid, 128, smem, stream>>>(a2);
         else
-            k_light_rays_split<true><<<grid, 128, smem, stream>>>(a2);
-    } else if (!plain && any_shadow) {
-        if (one_visit_env == 0)
-            k_light_rays_part<0, false><<<grid, 128, smem, stream>>>(a2);
-        else
-            k_light_rays_part<0, true><<<grid, 128, smem, stream>>>(a2);
-    } else if (!plain) {
-        if (one_visit_env == 0)
-            k_light_rays_part<1, false><<<grid, 128, smem, stream>>>(a2);
-        else
-            k_light_rays_part<1, true><<<grid, 128, smem, stream>>>(a2);
-    } else if (stats)
-        k_light_rays<true, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 4)
-        k_light_rays<false, 4><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 5)
-        k_light_rays<false, 5><<<grid, 128, smem, stream>>>(a2);
-    else if (minb == 7)
-        k_light_rays<false, 7><<<grid, 128, smem, stream>>>(a2);
-    else
-        k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (!queue) ++*launches;
+            k_light_rays<false, 6><<<grid, 128, smem, stream>>>(a2);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        ++*launches;
+    }
     if (rays_done && (e = cudaEventRecord(rays_done, stream)) != cudaSuccess) return e;
     ++*launches;
     if (!args.exact_math) return launch_light_shade_relaxed(stream, a2);

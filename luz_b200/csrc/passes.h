@@ -103,7 +103,10 @@ cudaError_t launch_volumetric_screen(cudaStream_t stream, const VolumetricArgs& 
 cudaError_t launch_volumetric_shadow_map(cudaStream_t stream, const VolumetricArgs& args);
 cudaError_t launch_shadow_map(cudaStream_t stream, const ShadowMapArgs& args);
 // ray kernel + shading kernel (light_pass.cu); the per-pixel visibility masks are cleared, written and read by it
-cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches);
+// aux / ev_fork / ev_join: a second stream and two events of the caller; the hint pass + shadow-ray launch run there while
+// the AO-ray launch runs on `stream`, joined before the shading kernel (all nullptr: one stream)
+cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool stats, cudaEvent_t rays_done, uint64_t* launches,
+                              cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 // exact: the bit-faithful build (LUZRT_DEBUG_EXACT_MATH) instead of the relaxed-precision one (relaxed.cu)
 cudaError_t launch_taa_pass(cudaStream_t stream, const TaaArgs& args, bool exact);
 cudaError_t launch_taa_relaxed(cudaStream_t stream, const TaaArgs& args);
