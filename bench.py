@@ -175,6 +175,7 @@ def run_ours(args):
             idt.copy_(torch.from_numpy(rt.comm_unique_id()))
         dist.broadcast(idt, 0)
         rt.comm_init(idt.cpu().numpy())
+    bvh_checked = False
 
     animate = cfg["animate"]
 
@@ -185,6 +186,9 @@ def run_ours(args):
     # frame 0 builds the TLAS, produces the G-buffer on the device (input producer) and seeds the history
     step(0, first=True)
     rt.sync()
+    if world > 1:  # every rank built its own replica of the BLASes / TLAS: check they are bitwise the same (collective)
+        rt.comm_check_bvh()
+        bvh_checked = True
 
     # one instrumented frame (outside the timed region): rays, nodes, triangles, instances per frame
     rt.set_debug(R.DEBUG_STATS)
@@ -439,6 +443,8 @@ def run_ours(args):
                              "ms": taa_ms},
             "l2_read_probe_gbs": l2_gbs,
         }
+        if bvh_checked:
+            out["bvh_identical_across_ranks"] = True  # luzrt_comm_check_bvh raised otherwise
         if parity:
             out["parity"] = parity
         if e2e:

@@ -136,6 +136,23 @@ LUZRT_API const char* luzrt_version(void);
 LUZRT_API int luzrt_comm_unique_id(void* out128);
 LUZRT_API int luzrt_comm_init(luzrt_ctx* ctx, const void* id128);
 
+/* One process, several GPUs (Luz is one process and one thread, main.cpp:356-366): creates n_devices contexts, ctx i on
+ * device_ids[i] with rank i of n_devices, and their communicators in one go (ncclCommInitAll; nothing to broadcast).
+ * out receives n_devices pointers; each is driven like any ctx (the same calls in the same order on every one, each
+ * followed through before the next is fine: calls are asynchronous) and destroyed with luzrt_destroy.  The two
+ * collectives of contexts that share a thread go through the _multi entry points (one NCCL group): */
+LUZRT_API int luzrt_create_multi(const int* device_ids, int n_devices, luzrt_ctx** out);
+LUZRT_API int luzrt_gather_multi(luzrt_ctx** ctxs, int n);           /* == luzrt_gather on every ctx          */
+LUZRT_API int luzrt_comm_check_bvh_multi(luzrt_ctx** ctxs, int n);   /* == luzrt_comm_check_bvh on every ctx  */
+
+/* Content hash of everything rays traverse on this ctx (TLAS nodes, leaf order, instance transforms and world boxes,
+ * nodes and triangles of every live BLAS).  Equal scenes give equal hashes on every run and every GPU. */
+LUZRT_API int luzrt_bvh_hash(luzrt_ctx* ctx, uint64_t* out);
+/* Collective over the communicator: every rank hashes its replica of the acceleration structures, the hashes are
+ * all-gathered and compared; LUZRT_E_STATE names the first rank that differs.  ("BVH build deterministic across GPUs":
+ * each rank builds its own replica instead of receiving a broadcast, so this is the check that they agree.) */
+LUZRT_API int luzrt_comm_check_bvh(luzrt_ctx* ctx);
+
 /* ---- resources ------------------------------------------------------------------------ */
 
 /* == DeferredRenderer::CreateImages(w, h) (DeferredRenderer.cpp:175-248): (re)allocates the

@@ -23,6 +23,9 @@ struct NcclApi {
     void* lib = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -35,10 +38,13 @@ struct NcclApi {
         if (!lib) return false;
         GetUniqueId = (decltype(GetUniqueId))dlsym(lib, "ncclGetUniqueId");
         CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        CommInitAll = (decltype(CommInitAll))dlsym(lib, "ncclCommInitAll");
+        GroupStart = (decltype(GroupStart))dlsym(lib, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(lib, "ncclGroupEnd");
         AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
         CommDestroy = (decltype(CommDestroy))dlsym(lib, "ncclCommDestroy");
         GetErrorString = (decltype(GetErrorString))dlsym(lib, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && AllGather && CommDestroy && GetErrorString;
+        return GetUniqueId && CommInitRank && CommInitAll && GroupStart && GroupEnd && AllGather && CommDestroy && GetErrorString;
     }
 };
 NcclApi g_nccl;
@@ -152,6 +158,7 @@ struct luzrt_ctx {
     DeviceStats* d_stats = nullptr;
     unsigned long long* d_lit = nullptr;
     float* d_pow22 = nullptr; // (c / 255)^2.2, c = 0..255 (light.frag:172), for the shading kernels
+    unsigned long long* d_hash = nullptr; // [0] content hash of this ctx's BVHs, [1 + r] the hash of rank r (luzrt_comm_check_bvh)
 
     cudaEvent_t ev[EV_COUNT][2]{};
     bool ev_valid[EV_COUNT]{};
@@ -406,7 +413,7 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints, c->d_pow22};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints, c->d_pow22, c->d_hash};
     for (float* p : c->shadow_data)
         if (p) cudaFree(p);
     for (void* p : ptrs)
@@ -444,6 +451,141 @@ int luzrt_comm_init(luzrt_ctx* c, const void* id128) {
     CU(c, cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming));
     CU(c, cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming));
     return LUZRT_OK;
+}
+
+// One process, n GPUs (Luz is one process and one thread, main.cpp:356-366): one ctx per device with
+// rank i of n, their communicators created together by ncclCommInitAll -- no unique id to broadcast.  Collectives of
+// contexts that live in one thread must be issued as one NCCL group: luzrt_gather_multi / luzrt_comm_check_bvh_multi.
+int luzrt_create_multi(const int* device_ids, int n_devices, luzrt_ctx** out) {
+    if (!device_ids || !out || n_devices < 1 || n_devices > 64) return LUZRT_E_INVALID;
+    for (int i = 0; i < n_devices; i++) out[i] = nullptr;
+    auto destroy_all = [&] {
+        for (int i = 0; i < n_devices; i++) {
+            if (out[i]) luzrt_destroy(out[i]);
+            out[i] = nullptr;
+        }
+    };
+    for (int i = 0; i < n_devices; i++) {
+        const int rc = luzrt_create(device_ids[i], i, n_devices, &out[i]);
+        if (rc != LUZRT_OK) {
+            destroy_all();
+            return rc;
+        }
+    }
+    if (n_devices == 1) return LUZRT_OK;
+    if (!g_nccl.load()) {
+        destroy_all();
+        return LUZRT_E_COMM;
+    }
+    std::vector<ncclComm_t> comms((size_t)n_devices);
+    if (g_nccl.CommInitAll(comms.data(), n_devices, device_ids) != ncclSuccess) {
+        destroy_all();
+        return LUZRT_E_COMM;
+    }
+    for (int i = 0; i < n_devices; i++) {
+        luzrt_ctx* c = out[i];
+        c->comm = comms[(size_t)i];
+        DeviceGuard g(c->device);
+        if (cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_resolved, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->ev_gathered, cudaEventDisableTiming) != cudaSuccess) {
+            destroy_all();
+            return LUZRT_E_CUDA;
+        }
+    }
+    return LUZRT_OK;
+}
+
+// Content hash of everything the rays traverse on this ctx: TLAS nodes, leaf order, instance transforms (the device
+// pointers in the records are skipped) and world boxes, and the nodes + triangles of every live BLAS.
+static int bvh_hash_enqueue(luzrt_ctx* c) {
+    REQUIRE(c, c->have_tlas, "no TLAS built");
+    if (!c->d_hash) CU(c, cudaMalloc(&c->d_hash, sizeof(unsigned long long) * 65));
+    unsigned long long* acc = c->d_hash;
+    CU(c, cudaMemsetAsync(acc, 0, sizeof(unsigned long long), c->stream));
+    CU(c, launch_hash_words(c->stream, c->tlas.nodes, (size_t)c->tlas.n_nodes * sizeof(WideNode), 0x11ull << 32, 4, 4, acc));
+    CU(c, launch_hash_words(c->stream, c->tlas.prim_order, (size_t)c->n_inst * 4, 0x22ull << 32, 4, 4, acc));
+    CU(c, launch_hash_words(c->stream, c->d_recs, (size_t)c->n_inst * sizeof(InstanceRec), 0x33ull << 32, sizeof(InstanceRec), 48, acc));
+    CU(c, launch_hash_words(c->stream, c->d_inst_boxes, (size_t)c->n_inst * 32, 0x44ull << 32, 4, 4, acc));
+    for (size_t i = 0; i < c->blas.size(); i++) {
+        const Blas& b = c->blas[i];
+        if (!b.alive) continue;
+        CU(c, launch_hash_words(c->stream, b.bvh.nodes, (size_t)b.bvh.n_nodes * sizeof(WideNode), (0x1000ull + i) << 32, 4, 4, acc));
+        CU(c, launch_hash_words(c->stream, b.tris, (size_t)b.n_tris * sizeof(WideTri), (0x800000ull + i) << 32, 4, 4, acc));
+    }
+    return LUZRT_OK;
+}
+
+int luzrt_bvh_hash(luzrt_ctx* c, uint64_t* out) {
+    if (!c) return LUZRT_E_INVALID;
+    REQUIRE(c, out, "out is null");
+    DeviceGuard g(c->device);
+    int rc = bvh_hash_enqueue(c);
+    if (rc != LUZRT_OK) return rc;
+    unsigned long long h = 0;
+    CU(c, cudaMemcpyAsync(&h, c->d_hash, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *out = h;
+    return LUZRT_OK;
+}
+
+// "BVH build must be deterministic across GPUs": every rank hashes its replica, one all-gather of the 8-byte hashes, and
+// every rank compares.  Collective: all ranks call it (contexts of one process through luzrt_comm_check_bvh_multi).
+static int check_bvh_enqueue(luzrt_ctx* c) {
+    if (!c->comm) return fail(c, LUZRT_E_STATE, "luzrt_comm_init has not been called");
+    int rc = bvh_hash_enqueue(c);
+    if (rc != LUZRT_OK) return rc;
+    const ncclResult_t r = g_nccl.AllGather(c->d_hash, c->d_hash + 1, 1, ncclUint64, c->comm, c->stream);
+    if (r != ncclSuccess) return fail(c, LUZRT_E_COMM, "ncclAllGather: %s", g_nccl.GetErrorString(r));
+    return LUZRT_OK;
+}
+static int check_bvh_compare(luzrt_ctx* c) {
+    unsigned long long h[65];
+    REQUIRE(c, c->world <= 64, "world > 64");
+    CU(c, cudaMemcpyAsync(h, c->d_hash, sizeof(unsigned long long) * (size_t)(1 + c->world), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < c->world; r++)
+        if (h[1 + r] != h[0])
+            return fail(c, LUZRT_E_STATE, "acceleration structures differ: rank %d has hash %016llx, rank %d has %016llx", c->rank,
+                        h[0], r, h[1 + r]);
+    return LUZRT_OK;
+}
+int luzrt_comm_check_bvh(luzrt_ctx* c) {
+    if (!c) return LUZRT_E_INVALID;
+    if (c->world == 1) return LUZRT_OK;
+    DeviceGuard g(c->device);
+    const int rc = check_bvh_enqueue(c);
+    return rc != LUZRT_OK ? rc : check_bvh_compare(c);
+}
+int luzrt_comm_check_bvh_multi(luzrt_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return LUZRT_E_INVALID;
+    if (n == 1) return luzrt_comm_check_bvh(ctxs[0]);
+    if (!g_nccl.load()) return LUZRT_E_COMM;
+    g_nccl.GroupStart();
+    int rc = LUZRT_OK;
+    for (int i = 0; i < n && rc == LUZRT_OK; i++) {
+        DeviceGuard g(ctxs[i]->device);
+        rc = check_bvh_enqueue(ctxs[i]);
+    }
+    const ncclResult_t r = g_nccl.GroupEnd();
+    if (rc == LUZRT_OK && r != ncclSuccess) rc = fail(ctxs[0], LUZRT_E_COMM, "ncclGroupEnd: %s", g_nccl.GetErrorString(r));
+    for (int i = 0; i < n && rc == LUZRT_OK; i++) {
+        DeviceGuard g(ctxs[i]->device);
+        rc = check_bvh_compare(ctxs[i]);
+    }
+    return rc;
+}
+
+int luzrt_gather_multi(luzrt_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return LUZRT_E_INVALID;
+    if (n == 1) return luzrt_gather(ctxs[0]);
+    if (!g_nccl.load()) return LUZRT_E_COMM;
+    g_nccl.GroupStart();
+    int rc = LUZRT_OK;
+    for (int i = 0; i < n && rc == LUZRT_OK; i++) rc = luzrt_gather(ctxs[i]);
+    const ncclResult_t r = g_nccl.GroupEnd();
+    if (rc == LUZRT_OK && r != ncclSuccess) rc = fail(ctxs[0], LUZRT_E_COMM, "ncclGroupEnd: %s", g_nccl.GetErrorString(r));
+    return rc;
 }
 
 int luzrt_resize(luzrt_ctx* c, uint32_t width, uint32_t height) {

@@ -70,6 +70,10 @@ cudaError_t launch_instance_prepare(cudaStream_t stream, const InstanceIn* d_in,
 cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceRec* d_recs_in, const InstanceMeta* d_meta_in,
                                    const BoxF* d_boxes_in, const uint32_t* d_prim_order, uint32_t n,
                                    InstanceRec* d_recs_out, InstanceMeta* d_meta_out, float4* d_boxes_out);
+// Adds the content hash of `bytes` of device data to *d_acc (a zeroed u64 on the device): of every stride_bytes-long
+// record only the first take_bytes count (stride_bytes == take_bytes: everything).  Order independent, deterministic.
+cudaError_t launch_hash_words(cudaStream_t stream, const void* data, size_t bytes, uint64_t seed, size_t stride_bytes,
+                              size_t take_bytes, unsigned long long* d_acc);
 // Boxes permuted into leaf order (for refit).
 cudaError_t launch_box_gather(cudaStream_t stream, const BoxF* d_in, const uint32_t* d_prim_order, uint32_t n,
                               BoxF* d_out);

@@ -1008,6 +1008,37 @@ cudaError_t refit_wide_bvh(cudaStream_t stream, const BoxF* d_boxes, WideBvh& bv
     return cudaGetLastError();
 }
 
+// ---- content hash (cross-GPU determinism check) ---------------------------------------------------------------------
+// acc += sum_i odd(splitmix64(seed + i)) * (word_i + 1) mod 2^64: position dependent, and -- being a sum of integers --
+// independent of the order in which threads add their parts, so equal data gives an equal hash on every run and GPU.
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void k_hash_words(const uint32_t* __restrict__ w, size_t n, uint64_t seed, size_t stride_words, size_t take_words,
+                             unsigned long long* __restrict__ acc) {
+    // hashes the first take_words of every stride_words-long record (records with device pointers in their tail)
+    unsigned long long h = 0;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (i % stride_words >= take_words) continue;
+        h += (splitmix64(seed + i) | 1ull) * ((unsigned long long)w[i] + 1ull);
+    }
+    for (int off = 16; off; off >>= 1) h += __shfl_xor_sync(0xFFFFFFFFu, h, off);
+    if ((threadIdx.x & 31) == 0 && h) atomicAdd(acc, h);
+}
+
+cudaError_t launch_hash_words(cudaStream_t stream, const void* data, size_t bytes, uint64_t seed, size_t stride_bytes,
+                              size_t take_bytes, unsigned long long* d_acc) {
+    const size_t n = bytes / 4;
+    if (n == 0) return cudaSuccess;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, 148 * 8);
+    k_hash_words<<<blocks, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(data), n, seed, stride_bytes / 4, take_bytes / 4, d_acc);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_triangle_boxes(cudaStream_t stream, const uint8_t* v, uint32_t stride, const uint32_t* idx,
                                   uint32_t n_tris, BoxF* boxes) {
     if (n_tris) k_triangle_boxes<<<div_up(n_tris, 256), 256, 0, stream>>>(v, stride, idx, n_tris, boxes);

@@ -26,7 +26,8 @@ EXPORTS = [
     "luzrt_sync", "luzrt_stream", "luzrt_launch_count", "luzrt_read_rows", "luzrt_owned_bands", "luzrt_read_owned",
     "luzrt_prefetch_gbuffer", "luzrt_flip_gbuffer", "luzrt_read_owned_async", "luzrt_read_wait",
     "luzrt_probe_read_bandwidth", "luzrt_volumetric_pass", "luzrt_shadow_map_pass",
-    "luzrt_read_shadow_map",
+    "luzrt_read_shadow_map", "luzrt_create_multi", "luzrt_gather_multi", "luzrt_comm_check_bvh_multi", "luzrt_bvh_hash",
+    "luzrt_comm_check_bvh",
 ]
 
 
@@ -87,6 +88,11 @@ def load_library():
         "luzrt_read_owned_async": (i32, [vp, i32, vp, C.c_size_t]),
         "luzrt_read_wait": (i32, [vp]),
         "luzrt_probe_read_bandwidth": (i32, [vp, C.c_size_t, i32, C.POINTER(C.c_double)]),
+        "luzrt_create_multi": (i32, [C.POINTER(i32), i32, C.POINTER(vp)]),
+        "luzrt_gather_multi": (i32, [C.POINTER(vp), i32]),
+        "luzrt_comm_check_bvh_multi": (i32, [C.POINTER(vp), i32]),
+        "luzrt_bvh_hash": (i32, [vp, C.POINTER(u64)]),
+        "luzrt_comm_check_bvh": (i32, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -94,6 +100,37 @@ def load_library():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def create_multi(device_ids):
+    """One process, several GPUs: [LuzRT] with rank i on device_ids[i], communicators initialised (luzrt_create_multi)."""
+    lib = load_library()
+    n = len(device_ids)
+    ids = (C.c_int * n)(*device_ids)
+    hs = (C.c_void_p * n)()
+    rc = lib.luzrt_create_multi(ids, n, hs)
+    if rc != 0:
+        raise LuzError(rc, "luzrt_create_multi failed")
+    return [LuzRT(device=device_ids[i], rank=i, world=n, _handle=C.c_void_p(hs[i])) for i in range(n)]
+
+
+def _group(ctxs):
+    arr = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    return arr, len(ctxs)
+
+
+def gather_multi(ctxs):
+    arr, n = _group(ctxs)
+    rc = load_library().luzrt_gather_multi(arr, n)
+    if rc != 0:
+        raise LuzError(rc, ctxs[0].lib.luzrt_last_error(ctxs[0].h).decode())
+
+
+def comm_check_bvh_multi(ctxs):
+    arr, n = _group(ctxs)
+    rc = load_library().luzrt_comm_check_bvh_multi(arr, n)
+    if rc != 0:
+        raise LuzError(rc, "; ".join(c.lib.luzrt_last_error(c.h).decode() for c in ctxs))
 
 
 def _ptr(a):
@@ -110,12 +147,15 @@ def _ptr(a):
 class LuzRT:
     """One context == one GPU.  Method names follow the C ABI one to one."""
 
-    def __init__(self, device=0, rank=0, world=1):
+    def __init__(self, device=0, rank=0, world=1, _handle=None):
         self.lib = load_library()
-        h = C.c_void_p()
-        rc = self.lib.luzrt_create(device, rank, world, C.byref(h))
-        if rc != 0:
-            raise LuzError(rc, "luzrt_create failed (no usable sm_100 GPU?)")
+        if _handle is not None:  # a ctx made by luzrt_create_multi
+            h = _handle
+        else:
+            h = C.c_void_p()
+            rc = self.lib.luzrt_create(device, rank, world, C.byref(h))
+            if rc != 0:
+                raise LuzError(rc, "luzrt_create failed (no usable sm_100 GPU?)")
         self.h = h
         self.width = self.height = 0
         self.rank, self.world = rank, world
@@ -245,6 +285,15 @@ class LuzRT:
     def comm_init(self, id128):
         id128 = np.ascontiguousarray(id128, dtype=np.uint8)
         self._ck(self.lib.luzrt_comm_init(self.h, _ptr(id128)))
+
+    def bvh_hash(self):
+        h = C.c_uint64(0)
+        self._ck(self.lib.luzrt_bvh_hash(self.h, C.byref(h)))
+        return h.value
+
+    def comm_check_bvh(self):
+        """Collective: raises if any rank's acceleration structures differ from this rank's."""
+        self._ck(self.lib.luzrt_comm_check_bvh(self.h))
 
     def stream(self):
         s = C.c_uint64(0)
