@@ -330,10 +330,39 @@ def run_ours(args):
         t_last = rt.read(R.TIMINGS)
         e2e = {"ms": e2e_ms, "serial_ms": serial_ms, "n_pipe": n_pipe, "light_ms": t_last.light_ms, "taa_ms": t_last.taa_ms, "h2d": strips.h2d_bytes(rank, world, W, Hh), "d2h": own_rows * W * 16}
 
+        # The frame as Luz's own RenderFrame crosses the boundary (SURVEY 8b "data crossing"): the host hands over the
+        # scene block, the model blocks and the instance transforms (GPUScene::UpdateResources[GPU]), the G-buffer is
+        # produced on the device by the opaque pass, and the host reads the composed BGRA8 rows it owns (4 B/px).  Every
+        # step uploads its inputs and reads its result; the TLAS is refit (the transforms do not change in this workload).
+        comp_host = torch.empty((own_rows, W, 4), dtype=torch.uint8, pin_memory=True)
+        n_inst = len(app.instances())
+
+        def scene_step():
+            wl.move(wl.frame)
+            app.render_frame(H.FRAME_OPAQUE | H.FRAME_COMPOSE | (0 if animate == "rebuild" else H.FRAME_TLAS_REFIT))
+            wl.frame += 1
+            rt.read_owned(R.IMG_COMPOSE, comp_host.numpy())
+
+        for i in range(3):
+            scene_step()
+        barrier()
+        n_scene = max(3, min(args.steps, 30))
+        t0 = time.perf_counter()
+        for i in range(n_scene):
+            scene_step()
+        rt.sync()
+        barrier()
+        t_scene = rt.read(R.TIMINGS)
+        e2e["scene_ms"] = (time.perf_counter() - t0) * 1e3 / n_scene
+        e2e["scene_h2d"] = 31200 + 128 * n_inst + 72 * n_inst  # SceneBlock + ModelBlock[] + luzrt_instance[]
+        e2e["scene_d2h"] = own_rows * W * 4
+        e2e["scene_gbuffer_ms"] = t_scene.gbuffer_ms
+
     ms_per_step = total_ms / args.steps
     vals = torch.tensor([ms_per_step, float(st.rays), e2e["ms"] if e2e else 0.0, kavg["light_ms"], kavg["taa_ms"],
                          kavg["gather_ms"], kavg["tlas_ms"], float(st.nodes_visited), float(st.triangles_tested),
-                         float(st.instances_entered), float(st.lit_pixels)], dtype=torch.float64, device="cuda")
+                         float(st.instances_entered), float(st.lit_pixels), e2e["scene_ms"] if e2e else 0.0],
+                        dtype=torch.float64, device="cuda")
     if world > 1:
         mx = vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -456,6 +485,13 @@ def run_ours(args):
                           "kernels_ms_under_copies": {"light": e2e["light_ms"], "taa": e2e["taa_ms"]},
                           "h2d_bytes_per_step": int(e2e["h2d"]), "d2h_bytes_per_step": int(e2e["d2h"]),
                           "host_numa_binding": numa_note}
+            out["e2e_scene"] = {"value": rays_frame / float(mx[11]) / 1e3, "unit": "Mrays/s", "ms_per_step": float(mx[11]),
+                                "mode": "the frame as Luz's RenderFrame crosses the boundary: scene block + model blocks + instance "
+                                        "transforms in (UpdateResources[GPU], TLAS refit), G-buffer produced on the device (opaque pass, "
+                                        "inside the timed region, not part of the ray count), composed BGRA8 rows of this rank out; "
+                                        "blocking read-back every step",
+                                "h2d_bytes_per_step": int(e2e["scene_h2d"]), "d2h_bytes_per_step": int(e2e["scene_d2h"]),
+                                "gbuffer_ms": e2e["scene_gbuffer_ms"]}
         if cpu_base:
             out["cpu_baseline"] = cpu_base
         print(json.dumps(out), flush=True)

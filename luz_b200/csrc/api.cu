@@ -1222,7 +1222,15 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
         return !(e && e[0] == '0');
     }();
     if (hints_env && !(c->debug & LUZRT_DEBUG_NO_HINTS) && c->fc.shadow_type == LUZW_SHADOW_RAYTRACING && c->fc.num_lights > 0) {
-        const size_t tiles = (size_t)((c->w + 15) / 16) * ((a.rows.rows + 7) / 8) * a.rows.n_bands;
+        // hint tiles of 16 x 8 pixels; one hint per warp tile (8 x 4) was measured and lost: four times the hint rays for
+        // a fallback rate that barely moves (C3 rays 4.15 -> 4.26 ms, C4 71.7 -> 75.0; LUZRT_HINT_TILE=8x4 for A/B runs)
+        static const bool fine = [] {
+            const char* e = getenv("LUZRT_HINT_TILE");
+            return e && e[0] == '8';
+        }();
+        a.hint_sx = fine ? 3u : 4u;
+        a.hint_sy = fine ? 2u : 3u;
+        const size_t tiles = (size_t)((c->w + (1u << a.hint_sx) - 1u) >> a.hint_sx) * ((a.rows.rows + (1u << a.hint_sy) - 1u) >> a.hint_sy) * a.rows.n_bands;
         int rc;
         if ((rc = grow(c, c->d_hints, c->hints_cap, tiles * (size_t)c->fc.num_lights)) != LUZRT_OK) return rc;
         a.hints = c->d_hints;

@@ -167,6 +167,12 @@ __device__ __forceinline__ uint32_t storage_row(const FrameConst& fc, uint32_t y
     return (b & ((1u << fc.world_shift) - 1u)) * fc.rows_per_rank + (b >> fc.world_shift) * fc.band_rows +
            (y - b * fc.band_rows);
 }
+// index of the occluder-hint tile of pixel (x, row r of band z) in a hint grid of (1 << sx) x (1 << sy)-pixel tiles
+__device__ __forceinline__ size_t hint_tile_index(const FrameConst& fc, const BandSet& bs, uint32_t sx, uint32_t sy, uint32_t z,
+                                                  uint32_t x, uint32_t r) {
+    const uint32_t hx = (fc.width + (1u << sx) - 1u) >> sx, hy = (bs.rows + (1u << sy) - 1u) >> sy;
+    return (size_t)(z * hy + (r >> sy)) * hx + (x >> sx);
+}
 __device__ __forceinline__ uint32_t band_row(const FrameConst& fc, const BandSet& bs, uint32_t z, uint32_t r) {
     int y = bs.first + (int)(z * bs.pitch + r);
     if (y < 0) y += (int)fc.height;

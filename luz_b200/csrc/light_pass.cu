@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(128) k_shadow_hints(const LightArgs a, uint32_
     if (valid) {
         const uint32_t light = g / n_tiles, tile = g % n_tiles; // a warp = 32 neighbouring tiles, one light
         const uint32_t bx = tile % tiles_x, by = (tile / tiles_x) % tiles_y, band = tile / (tiles_x * tiles_y);
-        const uint32_t x = min(bx * 16u + 8u, fc.width - 1u), r = min(by * 8u + 4u, a.rows.rows - 1u);
+        const uint32_t x = min((bx << a.hint_sx) + (1u << a.hint_sx) / 2u, fc.width - 1u);
+        const uint32_t r = min((by << a.hint_sy) + (1u << a.hint_sy) / 2u, a.rows.rows - 1u);
         const uint32_t y = band_row(fc, a.rows, band, r);
         const size_t pix = (size_t)y * fc.width + x;
         const float4 n4 = __ldg(a.normal + pix);
@@ -196,7 +197,6 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
     const bool in_image = x < fc.width && r < a.rows.rows;
     const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
     const size_t pix = (size_t)y * fc.width + x;
-    const uint32_t tile = (band * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; // index of the tile's occluder hints
 
     float3 N = f3(0.0f, 0.0f, 0.0f);
     float depth = 1.0f;
@@ -284,7 +284,7 @@ __device__ __forceinline__ void light_rays_body(const LightArgs& a, const uint32
                 radius = L4.radius;
                 shadow_ray_frame(L4, fragPos, N, camDist, O, C);
                 if (a.hints) { // the tile's occluder hint for this light is tried first (see k_shadow_hints)
-                    const uint32_t hint = __ldg(a.hints + (size_t)tile * (uint32_t)fc.num_lights + (uint32_t)(base + li));
+                    const uint32_t hint = __ldg(a.hints + hint_tile_index(fc, a.rows, a.hint_sx, a.hint_sy, band, x, r) * (uint32_t)fc.num_lights + (uint32_t)(base + li));
                     if (hint != kNoInstance) {
                         s_cand[0] = hint;
                         n_cand = 1;
@@ -379,7 +379,6 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const
     const FrameConst& fc = a.fc;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw) + warp * (kMaxCand * 32) + lane; // candidate lists [k][lane]
-    const uint32_t hints_x = (fc.width + 15u) / 16u, hints_y = (a.rows.rows + 7u) / 8u;
     const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
     const bool shadows = fc.shadow_type == LUZW_SHADOW_RAYTRACING && fc.num_lights > 0;
     uint2 stack[LUZ_STACK_SIZE];
@@ -413,7 +412,7 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const
             const float3 fragPos = depth_to_world(fc, u, v, depth);
             const float camDist = length3(fragPos - camPos);
             const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
-            const size_t hint_base = (size_t)((band * hints_y + (by >> 1)) * hints_x + (bx >> 1)) * (uint32_t)fc.num_lights;
+            const size_t hint_base = hint_tile_index(fc, a.rows, a.hint_sx, a.hint_sy, band, bx * 8u, by * 4u) * (uint32_t)fc.num_lights;
             BitWriter bits;
             bits.words = a.shadow_mask + pix * a.shadow_words;
             // one loop over the ray sources (the lights, then AO) so that the kernel holds one inlined copy of the traversal
@@ -526,12 +525,14 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
     const bool persistent = !stats && kernel_env == 0 && (any_shadow || any_ao);
     const dim3 grid((args.fc.width + 15) / 16, (args.rows.rows + 7) / 8, args.rows.n_bands); // 16x8 tiles: hints, plain kernel
     if (!(any_shadow && args.hints)) a2.hints = nullptr;
-    auto launch_hints = [&](cudaStream_t st) -> cudaError_t { // one hint ray per tile and light
-        const uint32_t n = grid.x * grid.y * args.rows.n_bands * (uint32_t)args.fc.num_lights;
+    auto launch_hints = [&](cudaStream_t st) -> cudaError_t { // one hint ray per hint tile and light
+        const uint32_t hx = (args.fc.width + (1u << args.hint_sx) - 1u) >> args.hint_sx;
+        const uint32_t hy = (args.rows.rows + (1u << args.hint_sy) - 1u) >> args.hint_sy;
+        const uint32_t n = hx * hy * args.rows.n_bands * (uint32_t)args.fc.num_lights;
         if (stats)
-            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, grid.x, grid.y);
+            k_shadow_hints<true><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, hx, hy);
         else
-            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, grid.x, grid.y);
+            k_shadow_hints<false><<<(n + 127) / 128, 128, 0, st>>>(a2, a2.hints, hx, hy);
         ++*launches;
         return cudaGetLastError();
     };

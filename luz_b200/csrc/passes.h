@@ -29,6 +29,7 @@ struct LightArgs {
     uint32_t count_row_begin, count_row_end; // rows (relative to a band's first row) whose lit pixels are counted
     uint32_t cand_offset;                    // byte offset of the AO candidate lists in dynamic shared memory
     uint32_t* hints;                         // occluder hints [tile][light] of the shadow rays (nullptr: none), light_pass.cu
+    uint32_t hint_sx, hint_sy;               // a hint tile is (1 << hint_sx) x (1 << hint_sy) pixels: 16 x 8 or 8 x 4
     uint32_t* tile_counter;                  // work counter of the persistent ray kernel (reset per launch)
     const ShadowMapRec* shadow_maps;         // per light, scene order (read only when fc.shadow_type == LUZW_SHADOW_MAP)
     const float* pow22;                      // 256 floats: (c / 255)^2.2 (launch_pow22_table)

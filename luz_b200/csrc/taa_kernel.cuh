@@ -35,7 +35,8 @@ struct Img { // an RGBA32F light image in banded storage order (common.cuh: stor
     const FrameConst* fc;
     int w, h;
     __device__ __forceinline__ float4 texel(int x, int y) const { // x, y within one period of the image
-        return __ldg(p + (size_t)storage_row(*fc, (uint32_t)wrap1(y, h)) * w + wrap1(x, w));
+        const uint32_t yw = (uint32_t)wrap1(y, h);
+        return __ldg(p + (size_t)(fc->world_shift ? storage_row(*fc, yw) : yw) * w + wrap1(x, w)); // one GPU: natural rows
     }
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ TapRow load_row(const TaaArgs& a, const int xl, const
     const FrameConst& fc = a.fc;
     const int H = (int)fc.height, W = (int)fc.width;
     const uint32_t yw = (uint32_t)wrap1(y, H);
-    const float4* lp = a.light_in + (size_t)storage_row(fc, yw) * W;
+    const float4* lp = a.light_in + (size_t)(fc.world_shift ? storage_row(fc, yw) : yw) * W;
     const float* dp = a.depth + (size_t)yw * W;
     TapRow t;
     t.l = __ldg(lp + xl);
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_taa(const TaaArgs a) {
     const int ybase = a.rows.first + (int)(blockIdx.z * a.rows.pitch); // first row of this band
     const int n_rows = min(kTaaRows, (int)a.rows.rows - ry0);
 
-    const float ddx = fabsf(1.0f / sw), ddy = fabsf(1.0f / sh);
+    const float ddx = fabsf(fdiv<FAST>(1.0f, sw)), ddy = fabsf(fdiv<FAST>(1.0f, sh));
     const float wc = mitchell(sqrtf(2.0f)), we = mitchell(1.0f), w0 = mitchell(0.0f);
     float weightSum = 0.0f; // accumulated in the shader's tap order (taa.comp:56-82)
     weightSum += wc; weightSum += we; weightSum += wc; weightSum += we; weightSum += w0;
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_taa(const TaaArgs a) {
         const int y = wrap1(ybase + ry0 + k, H);
         const TapRow bot = load_row(a, xl, x, xr, ybase + ry0 + k + 1);
 
-        const float su = ((float)x + 0.5f) / sw, sv = ((float)y + 0.5f) / sh; // get_uv
+        const float su = fdiv<FAST>((float)x + 0.5f, sw), sv = fdiv<FAST>((float)y + 0.5f, sh); // get_uv
         // find_closest_3x3: first strict minimum in row-major order
         int bi = -1, bj = -1;
         float dminz = top.dl;
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(256, kMinBlocks) k_taa(const TaaArgs a) {
             result = div_const4<FAST>(sourceSample * sourceWeight + historySample * historyWeight, wsum, fdiv<FAST>(1.0f, wsum));
             if (any_nan4(result)) result = sourceSample;
         }
-        a.out[(size_t)storage_row(fc, (uint32_t)y) * W + x] = result;
+        a.out[(size_t)(fc.world_shift ? storage_row(fc, (uint32_t)y) : (uint32_t)y) * W + x] = result;
         top = mid;
         mid = bot;
     }
