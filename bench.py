@@ -415,7 +415,9 @@ def run_ours(args):
         # roofline that applies to traversal is the L2 read bandwidth ("vs measured L2 or HBM peak as
         # applicable"), probed in this run; the unique-BLAS variant (~2 GB of BVH) streams from HBM.
         unique = args.variant == "unique"
-        trav_peak = hbm_peak if unique else l2_gbs
+        # (the unique-BLAS variant too: ncu shows its 1.9 GB of BVH served at 83 % L2 hit rate with 0.36 GB of DRAM traffic
+        # per launch -- a frame touches the visible surface regions only -- profiles/r2_unique_blas.md)
+        trav_peak = l2_gbs
         words = max((app.light_count() * cfg["light_samples"] + 31) // 32, 1) + max((cfg["ao_samples"] + 31) // 32, 1)
         rays_stream = (20.0 + 4.0 * words) * W * shade_rows     # normal 16 + depth 4 in, mask words out
         shade_stream = (48.0 + 4.0 * words) * W * shade_rows    # G-buffer 32 in, masks in, radiance 16 out
@@ -444,11 +446,14 @@ def run_ours(args):
             "clocks": clocks,
             # the dominant kernel (ray generation + any-hit traversal) against the memory level its working set lives in
             "roofline": {"kernel": "k_shadow_hints + ray kernel (k_light_rays_*: ray generation + any-hit traversal, the dominant "
-                                   "kernel), timed with CUDA events on the launch stream", "bound": "hbm" if unique else "l2",
+                                   "kernel), timed with CUDA events on the launch stream", "bound": "l2",
                          "achieved": (trav_bytes + rays_stream) / (rays_ms * 1e6), "peak": trav_peak, "unit": "GB/s",
                          "frac": (trav_bytes + rays_stream) / (rays_ms * 1e6) / trav_peak if trav_peak else None,
-                         "traffic": ncu_traffic(args, "light_rays", src_hash),
-                         "peak_source": hbm_src if unique else "luzrt_probe_read_bandwidth, 32 MiB L2-resident buffer, measured in this run",
+                         "traffic": (lambda a, b, c: (a + b + c) if None not in (a, b, c) else None)(
+                             ncu_traffic(args, "k_light_rays_persistent_shadow", src_hash),
+                             ncu_traffic(args, "k_light_rays_persistent_ao", src_hash), ncu_traffic(args, "k_shadow_hints", src_hash)),
+                         "peak_source": "luzrt_probe_read_bandwidth, 32 MiB L2-resident buffer, measured in this run",
+                         "ncu": ncu_counters(args, ("k_light_rays_persistent_shadow", "k_light_rays_persistent_ao", "k_shadow_hints"), src_hash),
                          "algorithmic_bytes": "SURVEY 8(d): per ray 80 B/node + 48 B/triangle + 64 B/instance (counted by the "
                                               "statistics variant of the same kernel on the same BVH and rays) + 20 B/px "
                                               "normal+depth in + 4 B/px per mask word out",
@@ -522,7 +527,21 @@ def ncu_traffic(args, kernel, src_hash):
         key = args.config + ("-" + args.variant if args.variant else "")
         if args.width or args.gpus != 1 or t.get("source_hash") != src_hash:
             return None
-        return t.get(key, {}).get(kernel)
+        v = t.get(key, {}).get(kernel)
+        return v.get("dram_bytes") if isinstance(v, dict) else v
+    except Exception:
+        return None
+
+
+def ncu_counters(args, kernels, src_hash):
+    """The committed ncu counters (active lanes, issue, L1 / L2 / DRAM throughput) of the named kernels, same staleness rule."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        key = args.config + ("-" + args.variant if args.variant else "")
+        if args.width or args.gpus != 1 or t.get("source_hash") != src_hash:
+            return None
+        return {k: t[key][k] for k in kernels if k in t.get(key, {})} or None
     except Exception:
         return None
 
