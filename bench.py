@@ -243,6 +243,20 @@ def run_ours(args):
         for k in kt:
             kt[k].append(getattr(t, k))
     kavg = {k: float(np.mean(v)) for k, v in kt.items()}
+    t_hint = rt.read(R.TIMINGS)
+    temporal = {"on": bool(t_hint.temporal_on), "settled_fraction": float(t_hint.temporal_settled)}
+    # the same frames without the per-ray temporal occluder hints (what the first frame after a cut costs; same bits)
+    rt.set_debug(R.DEBUG_NO_TEMPORAL)
+    cold = []
+    for i in range(min(args.steps, 6)):
+        step(0)
+        t = rt.read(R.TIMINGS)
+        cold.append((t.light_ms, t.light_rays_ms))
+    rt.set_debug(0)
+    for i in range(3):  # hints warm again before the end-to-end runs
+        step(0)
+    temporal["light_ms_without"] = float(np.mean([c[0] for c in cold[1:]]))
+    temporal["light_rays_ms_without"] = float(np.mean([c[1] for c in cold[1:]]))
 
     # ---- end to end through the C ABI with HOST buffers (G-buffer in, resolved frame out) ----
     own_rows = Hh // world
@@ -476,6 +490,10 @@ def run_ours(args):
                              "traffic": ncu_traffic(args, "k_taa", src_hash), "peak_source": hbm_src, "hbm_read_probe_gbs": hbm_probe,
                              "ms": taa_ms},
             "l2_read_probe_gbs": l2_gbs,
+            # per-ray temporal occluder hints (light_pass.cu k_shadow_rays_temporal): every shadow ray first tries the
+            # triangles that occluded the same ray in the last frames; exact (same bits), adaptive (off when few rays are
+            # settled); *_without = the same frames with LUZRT_DEBUG_NO_TEMPORAL
+            "temporal_hints": temporal,
         }
         if bvh_checked:
             out["bvh_identical_across_ranks"] = True  # luzrt_comm_check_bvh raised otherwise

@@ -89,6 +89,8 @@ enum {
                               bitmasks (they carry the rays' results to its shading kernel)            */
     LUZRT_DEBUG_STATS = 2, /* light pass counts nodes / triangles / instances per ray */
     LUZRT_DEBUG_NO_HINTS = 4, /* shadow rays descend from the TLAS root without trying the tile's occluder hint first */
+    LUZRT_DEBUG_NO_TEMPORAL = 16, /* shadow rays do not try the occluder they found last frame first (per-ray temporal hints
+                                    off: every frame costs what the first frame costs; same bits) */
     LUZRT_DEBUG_EXACT_MATH = 8 /* luzrt_light_pass / luzrt_taa_pass run the bit-faithful builds of the shading and resolve
                                   kernels (every operation of light.frag / taa.comp in the shader's order, IEEE division
                                   and square root, no FMA contraction) instead of the relaxed-precision ones a host gets
@@ -116,6 +118,9 @@ typedef struct luzrt_timings {
     float volumetric_ms; /* last luzrt_volumetric_pass ("VolumetricLightPass", main.cpp:274)    */
     float shadow_map_ms; /* last luzrt_shadow_map_pass ("ShadowMaps", main.cpp:260)              */
     float light_rays_ms; /* the ray kernel's share of light_ms (mask clears + k_light_rays)      */
+    float temporal_settled; /* fraction of the shadow rays of the last measured frame that their temporal occluder hints
+                               settled (-1: never measured); temporal_on: 1 if the last light pass used the hints */
+    float temporal_on;
 } luzrt_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

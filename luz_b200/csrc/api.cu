@@ -134,6 +134,7 @@ struct luzrt_ctx {
     WideBvh tlas;
     bool have_tlas = false;
     InstanceIn* d_inst_in = nullptr;
+    uint32_t* d_inst_inv = nullptr; // leaf position of input instance i (inverse of tlas.prim_order)
     InstanceRec *d_recs_in = nullptr, *d_recs = nullptr;
     InstanceMeta *d_meta_in = nullptr, *d_meta = nullptr;
     float4* d_inst_boxes = nullptr; // 2 per instance, TLAS leaf order
@@ -158,6 +159,22 @@ struct luzrt_ctx {
     DeviceStats* d_stats = nullptr;
     unsigned long long* d_lit = nullptr;
     float* d_pow22 = nullptr; // (c / 255)^2.2, c = 0..255 (light.frag:172), for the shading kernels
+    uint2* d_ray_hints = nullptr; // per-ray temporal occluder hints of the shadow rays, [shadow bit][pixel][slots] (light_pass.cu)
+    size_t ray_hints_cap = 0;     // in uint2 elements
+    // the hints pay when last frame's occluders still occlude (static or slowly changing views) and cost a few per cent
+    // when they do not (every instance moving every frame): the kernel counts how many rays they settle, the counters
+    // come back asynchronously, and the pass uses the hints while the settled fraction stays above a threshold; while it
+    // is off, two consecutive frames out of 32 run with hints (the first refreshes them, the second measures)
+    unsigned long long* d_temporal_cnt = nullptr; // 64 x 16 u64
+    unsigned long long* h_temporal_cnt = nullptr; // pinned copy
+    cudaEvent_t ev_temporal = nullptr;
+    bool temporal_pending = false; // a copy of the counters is in flight
+    bool temporal_use = true;
+    uint32_t temporal_frame = 0;
+    float temporal_rate = -1.0f;   // last measured settled fraction
+    bool temporal_last_on = false; // the last light pass ran the temporal-hint kernel
+    uint32_t temporal_consecutive = 0;  // consecutive light passes that ran it
+    bool temporal_pending_warm = false; // the counters in flight belong to a frame whose hints the frame before had written
     unsigned long long* d_hash = nullptr; // [0] content hash of this ctx's BVHs, [1 + r] the hash of rank r (luzrt_comm_check_bvh)
 
     cudaEvent_t ev[EV_COUNT][2]{};
@@ -413,7 +430,9 @@ void luzrt_destroy(luzrt_ctx* c) {
     if (c->unperm) cudaFree(c->unperm);
     void* ptrs[] = {c->blue_noise, c->d_lights, c->d_boxes,   c->d_blas_attr, c->d_inst_in, c->d_recs_in,
                     c->d_recs,     c->d_meta_in, c->d_meta,   c->d_tex_data,  c->d_tex_size, c->d_models, c->d_inst_boxes,
-                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints, c->d_pow22, c->d_hash};
+                    c->d_shadow_mask, c->d_ao_mask, c->d_stats, c->d_lit, c->d_vol_lights, c->d_shadow_recs, c->d_hints, c->d_pow22, c->d_hash, c->d_ray_hints, c->d_inst_inv, c->d_temporal_cnt};
+    if (c->h_temporal_cnt) cudaFreeHost(c->h_temporal_cnt);
+    if (c->ev_temporal) cudaEventDestroy(c->ev_temporal);
     for (float* p : c->shadow_data)
         if (p) cudaFree(p);
     for (void* p : ptrs)
@@ -815,6 +834,8 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
         in.blas_bounds = b.bounds;
         in.custom_index = instances[i].custom_index;
         in.blas_slot = h;
+        in.n_tris = b.n_tris;
+        in.pad = 0;
         max_blas_levels = std::max(max_blas_levels, b.levels);
         if (same_set && c->last_blas[i] != h) same_set = false;
     }
@@ -822,13 +843,14 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     const size_t cap_need = std::max<uint32_t>(count, 1);
     if (c->inst_cap < cap_need) {
         CU(c, cudaStreamSynchronize(c->stream));
-        void* olds[] = {c->d_inst_in, c->d_recs_in, c->d_recs, c->d_meta_in, c->d_meta, c->d_inst_boxes};
+        void* olds[] = {c->d_inst_in, c->d_recs_in, c->d_recs, c->d_meta_in, c->d_meta, c->d_inst_boxes, c->d_inst_inv};
         for (void* p : olds)
             if (p) cudaFree(p);
         c->d_inst_in = nullptr;
         c->d_recs_in = c->d_recs = nullptr;
         c->d_meta_in = c->d_meta = nullptr;
         c->d_inst_boxes = nullptr;
+        c->d_inst_inv = nullptr;
         c->inst_cap = 0;
         const size_t n = cap_need + cap_need / 2;
         CU(c, cudaMalloc(&c->d_inst_in, n * sizeof(InstanceIn)));
@@ -837,6 +859,7 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
         CU(c, cudaMalloc(&c->d_meta_in, n * sizeof(InstanceMeta)));
         CU(c, cudaMalloc(&c->d_meta, n * sizeof(InstanceMeta)));
         CU(c, cudaMalloc(&c->d_inst_boxes, n * 2 * sizeof(float4)));
+        CU(c, cudaMalloc(&c->d_inst_inv, n * sizeof(uint32_t)));
         c->inst_cap = n;
     }
     int rc;
@@ -852,8 +875,8 @@ int luzrt_tlas_build(luzrt_ctx* c, const luzrt_instance* instances, uint32_t cou
     } else {
         CU(c, build_wide_bvh(c->stream, c->scratch, c->d_boxes, count, 1, c->tlas, &c->launches));
     }
-    CU(c, launch_instance_gather(c->stream, c->d_recs_in, c->d_meta_in, c->d_boxes, c->tlas.prim_order, count, c->d_recs,
-                                 c->d_meta, c->d_inst_boxes));
+    CU(c, launch_instance_gather(c->stream, c->d_inst_in, c->d_recs_in, c->d_meta_in, c->d_boxes, c->tlas.prim_order, count, c->d_recs,
+                                 c->d_meta, c->d_inst_boxes, c->d_inst_inv));
     c->launches += count ? 1 : 0;
     ev_end(c, EV_TLAS);
     c->n_inst = count;
@@ -1235,6 +1258,66 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
         if ((rc = grow(c, c->d_hints, c->hints_cap, tiles * (size_t)c->fc.num_lights)) != LUZRT_OK) return rc;
         a.hints = c->d_hints;
     }
+    a.ray_hints = nullptr;
+    a.n_instances = c->n_inst;
+    a.inst_order = c->tlas.prim_order;
+    a.inst_leaf = c->d_inst_inv;
+    {   // per-ray temporal occluder hints: 16 bytes per shadow ray of the frame, kept from frame to frame.  They never need
+        // invalidating (an entry is bounds-checked and then only decides which triangle is tried first), so a resize or a
+        // different light count just starts from a cleared array.  LUZRT_TEMPORAL_HINTS=0 / LUZRT_DEBUG_NO_TEMPORAL: off;
+        // LUZRT_TEMPORAL_HINTS_MB: memory budget (default 24 GB of the 180).
+        static const long budget_mb = [] {
+            const char* e = getenv("LUZRT_TEMPORAL_HINTS");
+            if (e && e[0] == '0') return 0L;
+            const char* m = getenv("LUZRT_TEMPORAL_HINTS_MB");
+            return m ? atol(m) : 24576L;
+        }();
+        const size_t need = (size_t)c->shadow_bits * px * (c->shadow_mask_words <= 2 ? 2u : 1u); // two slots per ray up to 64 rays per pixel
+        if (budget_mb > 0 && !(c->debug & LUZRT_DEBUG_NO_TEMPORAL) && c->shadow_bits > 0 && c->shadow_mask_words <= 8 &&
+            c->fc.shadow_type == LUZW_SHADOW_RAYTRACING && need * sizeof(uint2) <= (size_t)budget_mb << 20) {
+            if (c->ray_hints_cap != need) { // (re)allocate and clear: all entries out of bounds
+                CU(c, cudaStreamSynchronize(c->stream));
+                if (c->d_ray_hints) cudaFree(c->d_ray_hints);
+                c->d_ray_hints = nullptr;
+                c->ray_hints_cap = 0;
+                if (cudaMalloc(&c->d_ray_hints, need * sizeof(uint2)) != cudaSuccess) return fail(c, LUZRT_E_NOMEM, "ray hints: %zu bytes", need * sizeof(uint2));
+                c->ray_hints_cap = need;
+                CU(c, cudaMemsetAsync(c->d_ray_hints, 0xFF, need * sizeof(uint2), c->stream));
+            }
+            if (!c->d_temporal_cnt) {
+                CU(c, cudaMalloc(&c->d_temporal_cnt, 64 * 16 * sizeof(unsigned long long)));
+                CU(c, cudaMallocHost(&c->h_temporal_cnt, 64 * 16 * sizeof(unsigned long long)));
+                CU(c, cudaEventCreateWithFlags(&c->ev_temporal, cudaEventDisableTiming));
+            }
+            if (c->temporal_pending && cudaEventQuery(c->ev_temporal) == cudaSuccess) { // counters of an earlier frame have landed
+                unsigned long long fired = 0, settled = 0;
+                for (int i = 0; i < 64; i++) fired += c->h_temporal_cnt[16 * i], settled += c->h_temporal_cnt[16 * i + 1];
+                c->temporal_pending = false;
+                if (fired && c->temporal_pending_warm) { // (a frame whose hints were not written by the frame before says nothing)
+                    c->temporal_rate = (float)((double)settled / (double)fired);
+                    // hysteresis: on above 30 % settled, off below 20 % (C3 0.60, C2 0.24-0.39, C5 with every instance moving 0.17)
+                    if (c->temporal_rate >= 0.30f) c->temporal_use = true;
+                    else if (c->temporal_rate < 0.20f) c->temporal_use = false;
+                }
+            }
+            static const bool adaptive_env = [] { // LUZRT_TEMPORAL_HINTS=force: always on (A/B runs)
+                const char* e = getenv("LUZRT_TEMPORAL_HINTS");
+                return !(e && e[0] == 'f');
+            }();
+            c->temporal_frame++;
+            const bool probe = (c->temporal_frame & 31u) < 2u; // two frames out of 32
+            if (c->temporal_use || probe || !adaptive_env) {
+                a.ray_hints = c->d_ray_hints;
+                a.temporal_counters = c->d_temporal_cnt;
+            }
+            static const bool count_env = [] { // measurement aid (profiles/tools/temporal_stats.py)
+                const char* e = getenv("LUZRT_TEMPORAL_COUNT");
+                return e && e[0] == '1';
+            }();
+            a.count_temporal = count_env ? 1u : 0u;
+            if (count_env) CU(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), c->stream));
+        }
+    }
     a.count_row_begin = c->world == 1 ? 0u : 1u; // the halo rows are recomputation, not frame rays
     a.count_row_end = c->world == 1 ? c->h : 1u + c->band_rows;
     CU(c, wait_gather(c, a.out));
@@ -1248,7 +1331,17 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
         CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
+    const bool temporal_kernel = a.ray_hints && !stats && a.shadow_words <= 8;
+    c->temporal_last_on = temporal_kernel;
+    c->temporal_consecutive = temporal_kernel ? c->temporal_consecutive + 1u : 0u;
+    if (temporal_kernel) CU(c, cudaMemsetAsync(c->d_temporal_cnt, 0, 64 * 16 * sizeof(unsigned long long), c->stream));
     CU(c, launch_light_pass(c->stream, a, stats, c->ev[EV_LIGHT_RAYS][1], &c->launches, c->aux_stream, c->ev_fork, c->ev_join));
+    if (temporal_kernel && !c->temporal_pending) { // bring this frame's counters back without stalling anybody
+        CU(c, cudaMemcpyAsync(c->h_temporal_cnt, c->d_temporal_cnt, 64 * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->ev_temporal, c->stream));
+        c->temporal_pending = true;
+        c->temporal_pending_warm = c->temporal_consecutive >= 2u;
+    }
     c->ev_valid[EV_LIGHT_RAYS] = true;
     ev_end(c, EV_LIGHT);
     return LUZRT_OK;
@@ -1512,7 +1605,8 @@ int luzrt_read(luzrt_ctx* c, int which, void* dst, size_t bytes) {
         float ms[EV_COUNT] = {0};
         for (int i = 0; i < EV_COUNT; i++)
             if (c->ev_valid[i]) cudaEventElapsedTime(&ms[i], c->ev[i][0], c->ev[i][1]);
-        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC], ms[EV_SHADOWMAP], ms[EV_LIGHT_RAYS]};
+        luzrt_timings t{ms[EV_TLAS], ms[EV_GBUF], ms[EV_LIGHT], ms[EV_TAA], ms[EV_GATHER], ms[EV_COMPOSE], ms[EV_VOLUMETRIC], ms[EV_SHADOWMAP], ms[EV_LIGHT_RAYS],
+                        c->temporal_rate, c->temporal_last_on ? 1.0f : 0.0f};
         memcpy(dst, &t, sizeof(t));
         return LUZRT_OK;
     }

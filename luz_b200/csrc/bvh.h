@@ -62,14 +62,17 @@ struct InstanceIn {
     BoxF blas_bounds;
     uint32_t custom_index;
     uint32_t blas_slot;
+    uint32_t n_tris; // triangles of the BLAS (stored in the w of the instance's world box: bounds of per-ray occluder hints)
+    uint32_t pad;
 };
 // World boxes + inverse transforms for n instances (input order).
 cudaError_t launch_instance_prepare(cudaStream_t stream, const InstanceIn* d_in, uint32_t n, BoxF* d_boxes,
                                     InstanceRec* d_recs_in_order, InstanceMeta* d_meta_in_order);
 // Permutes records into TLAS leaf order.
-cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceRec* d_recs_in, const InstanceMeta* d_meta_in,
+cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceIn* d_in, const InstanceRec* d_recs_in, const InstanceMeta* d_meta_in,
                                    const BoxF* d_boxes_in, const uint32_t* d_prim_order, uint32_t n,
-                                   InstanceRec* d_recs_out, InstanceMeta* d_meta_out, float4* d_boxes_out);
+                                   InstanceRec* d_recs_out, InstanceMeta* d_meta_out, float4* d_boxes_out,
+                                   uint32_t* d_leaf_of_input /* n: inverse of d_prim_order */);
 // Adds the content hash of `bytes` of device data to *d_acc (a zeroed u64 on the device): of every stride_bytes-long
 // record only the first take_bytes count (stride_bytes == take_bytes: everything).  Order independent, deterministic.
 cudaError_t launch_hash_words(cudaStream_t stream, const void* data, size_t bytes, uint64_t seed, size_t stride_bytes,

@@ -766,18 +766,19 @@ __global__ void k_instance_prepare(const InstanceIn* __restrict__ in, uint32_t n
     boxes[i] = b;
 }
 
-__global__ void k_instance_gather(const InstanceRec* __restrict__ rin, const InstanceMeta* __restrict__ min_,
+__global__ void k_instance_gather(const InstanceIn* __restrict__ in, const InstanceRec* __restrict__ rin, const InstanceMeta* __restrict__ min_,
                                   const BoxF* __restrict__ bin, const uint32_t* __restrict__ order, uint32_t n,
                                   InstanceRec* __restrict__ rout, InstanceMeta* __restrict__ mout,
-                                  float4* __restrict__ bout) {
+                                  float4* __restrict__ bout, uint32_t* __restrict__ inv) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t src = order[k];
+    inv[src] = k; // leaf position of input instance src
     rout[k] = rin[src];
     mout[k] = min_[src];
     const BoxF b = bin[src];
     bout[2 * k] = make_float4(b.lox, b.loy, b.loz, 0.0f);
-    bout[2 * k + 1] = make_float4(b.hix, b.hiy, b.hiz, 0.0f);
+    bout[2 * k + 1] = make_float4(b.hix, b.hiy, b.hiz, __uint_as_float(in[src].n_tris)); // w: triangle count of the BLAS
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -1054,10 +1055,10 @@ cudaError_t launch_instance_prepare(cudaStream_t stream, const InstanceIn* in, u
     if (n) k_instance_prepare<<<div_up(n, 128), 128, 0, stream>>>(in, n, boxes, recs, meta);
     return cudaGetLastError();
 }
-cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceRec* rin, const InstanceMeta* min_,
+cudaError_t launch_instance_gather(cudaStream_t stream, const InstanceIn* in, const InstanceRec* rin, const InstanceMeta* min_,
                                    const BoxF* bin, const uint32_t* order, uint32_t n, InstanceRec* rout,
-                                   InstanceMeta* mout, float4* bout) {
-    if (n) k_instance_gather<<<div_up(n, 128), 128, 0, stream>>>(rin, min_, bin, order, n, rout, mout, bout);
+                                   InstanceMeta* mout, float4* bout, uint32_t* inv) {
+    if (n) k_instance_gather<<<div_up(n, 128), 128, 0, stream>>>(in, rin, min_, bin, order, n, rout, mout, bout, inv);
     return cudaGetLastError();
 }
 

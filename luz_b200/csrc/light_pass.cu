@@ -498,6 +498,220 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const
     }
 }
 
+// ---- shadow rays with per-ray temporal occluder hints ---------------------------------------------------------------------
+// 87 % of C3's shadow rays are occluded, and the ray a pixel fires towards a light this frame is -- up to the TAA jitter
+// and one step of the blue-noise sequence -- the ray it fired last frame.  The triangle that occluded it then very
+// probably occludes it now.  So every shadow ray remembers its last two occluders: ray_hints[bit][pixel] = 2 x (instance,
+// triangle) is written by whoever finds a hit, and the next frame's ray tests THOSE triangles first -- an instance
+// transform and a triangle test each, ~150 instructions against ~1900 for a hinted traversal, executed by all lit lanes of
+// the tile together.  Rays it does not settle go into a per-warp queue in shared memory (ballot + prefix popcount, as in the
+// compaction experiment of profiles/r2_ray_queue_experiment.md -- which lost because EVERY ray went through the queue;
+// here the queue only sees the few survivors) and are traced 32 at a time: tile hint first, then the TLAS root.
+// Exactness: a hint only changes the ORDER in which occluders are tried.  Whatever the hint array holds -- last frame's
+// occluders, the occluders of another scene, garbage -- an entry is either out of bounds (skipped) or names a real
+// triangle of a real instance, and a hit on it is a hit; a miss falls through to the full traversal.  The bits are those
+// of the kernels above on the first frame, on the hundredth, and after the scene has changed under the hints
+// (tests/test_gpu_parity.py::test_temporal_hints_do_not_change_visibility).  Used while a pixel has at most 256 shadow
+// rays (the masks of a tile are assembled in shared memory) and the hint array fits its budget; else the kernel above.
+constexpr int kShadowQueueCap = 64; // < 32 queued before a round, <= 32 pushed by it; a drain pops 32 (nothing is re-queued)
+// Two shapes: up to 64 shadow rays per pixel keep the last TWO occluders of every ray (16 bytes per ray); up to 256 (C4's
+// 256 lights) keep one (8 bytes per ray: 17 GB at 4K -- HBM is there to be used -- read once per frame at ~3 ms).
+template <uint32_t WORDS>
+struct __align__(16) ShadowQueue { // one per warp
+    float4 q0[kShadowQueueCap];   // O.xyz, tmax
+    float4 q1[kShadowQueueCap];   // dir.xyz, meta: owner lane | mask bit << 8
+    uint32_t aux[kShadowQueueCap]; // first candidate instance of the traversal (kNoInstance: none)
+    uint32_t mask[32 * WORDS];     // the shadow mask words of the tile's 32 pixels
+};
+
+template <bool ONE_VISIT, int MIN_BLOCKS, int SLOTS, uint32_t kSmemMaskWords>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_shadow_rays_temporal(const LightArgs a, uint32_t* __restrict__ tile_counter,
+                                                                          const uint32_t tiles_x, const uint32_t tiles_y,
+                                                                          const uint32_t n_tiles, uint2* __restrict__ ray_hints /* [bit][pixel][SLOTS] */,
+                                                                          const uint32_t n_inst) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ShadowQueue<kSmemMaskWords>& ws = reinterpret_cast<ShadowQueue<kSmemMaskWords>*>(smem_raw)[warp];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const size_t px_total = (size_t)fc.width * fc.height;
+    uint2 stack[LUZ_STACK_SIZE];
+
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t bx = t % tiles_x, by = (t / tiles_x) % tiles_y, band = t / (tiles_x * tiles_y);
+        const uint32_t x = bx * 8u + (lane & 7), r = by * 4u + (lane >> 3);
+        const bool in_image = x < fc.width && r < a.rows.rows;
+        const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
+        const size_t pix = (size_t)y * fc.width + x;
+        float3 N = f3(0.0f, 0.0f, 0.0f);
+        float depth = 1.0f;
+        uchar4 bn8 = make_uchar4(0, 0, 0, 0);
+        if (in_image) {
+            const float4 n4 = __ldg(a.normal + pix);
+            N = f3(n4.x, n4.y, n4.z);
+            depth = __ldg(a.depth + pix);
+            bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+        }
+        const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
+        if (!__any_sync(0xFFFFFFFFu, lit)) { // nothing to trace: the tile's masks are zero
+            if (in_image)
+                for (uint32_t w = 0; w < a.shadow_words; w++) a.shadow_mask[pix * a.shadow_words + w] = 0u;
+            continue;
+        }
+#pragma unroll
+        for (uint32_t w = 0; w < kSmemMaskWords; w++) ws.mask[lane * kSmemMaskWords + w] = 0u;
+        const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+        const float3 fragPos = depth_to_world(fc, u, v, depth);
+        const float camDist = length3(fragPos - camPos);
+        const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+        const size_t hint_base = hint_tile_index(fc, a.rows, a.hint_sx, a.hint_sy, band, bx * 8u, by * 4u) * (uint32_t)fc.num_lights;
+        __syncwarp();
+
+        int q_count = 0, light = 0, sample = 0;
+        uint32_t bit0 = 0; // first mask bit of the current light
+        bool producing = true;
+        uint32_t n_fired = 0, n_settled = 0; // this tile's shadow rays / those the temporal hints settled (feeds the host's on / off decision)
+        while (true) {
+            // ---- produce: one (light, sample) round for every lit lane; the temporal hint settles most of them at once ----
+            while (q_count < 32 && producing) {
+                if (light >= fc.num_lights) {
+                    producing = false;
+                    break;
+                }
+                const float4* lp = reinterpret_cast<const float4*>(a.lights + light); // same address in every lane
+                LightRec L4;
+                reinterpret_cast<float4*>(&L4)[0] = __ldg(lp + 0);
+                reinterpret_cast<float4*>(&L4)[1] = __ldg(lp + 1);
+                reinterpret_cast<float4*>(&L4)[2] = __ldg(lp + 2);
+                reinterpret_cast<float4*>(&L4)[3] = __ldg(lp + 3);
+                const int n_samples = L4.num_shadow_samples;
+                if (sample >= n_samples) { // no (more) rays for this light (light.frag:87-89)
+                    bit0 += (uint32_t)max(n_samples, 0);
+                    light++;
+                    sample = 0;
+                    continue;
+                }
+                const uint32_t bit = bit0 + (uint32_t)sample;
+                float3 O = f3(0.0f, 0.0f, 0.0f), dir = O;
+                float tMaxRay = 0.0f;
+                bool pending = false; // this lane's ray is not settled yet
+                bool fired = false;   // this lane has a (valid) ray in this round
+                uint32_t hint_own = kNoInstance;
+                if (lit) { // EvaluateShadow + TraceShadowRay (light.frag:137-146, :86-100)
+                    float3 C;
+                    shadow_ray_frame(L4, fragPos, N, camDist, O, C);
+                    const float3 T = rg_normalize(cross3(C, f3(0.0f, 1.0f, 0.0f)));
+                    const float3 B = rg_normalize(cross3(T, C));
+                    tMaxRay = rg_length(C);
+                    const float2 rng = blue_noise_sample(bn_r, bn_g, sample, fc.frame_mod);
+                    const float pointRadius = L4.radius * rg_sqrt(rng.x); // DiskSample (light.frag:57-61)
+                    float sn, cs;
+                    rg_sincos(rng.y * 2.0f * kPI, &sn, &cs);
+                    dir = rg_normalize(rg_combine(T, pointRadius * cs, B, pointRadius * sn, C, 1.0f));
+                    // rays with NaNs (the vertical-light tangent of light.frag:90) and null directions miss, as in trace_ray
+                    pending = (O.x == O.x && O.y == O.y && O.z == O.z && dir.x == dir.x && dir.y == dir.y && dir.z == dir.z &&
+                               tMaxRay == tMaxRay) && !(dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f);
+                    fired = pending;
+                    uint32_t own_inst = kNoInstance; // the instance that occluded this ray last time: first candidate if it has to be traced
+                    if (pending) { // the last two occluders of this very ray, most recent first
+                        uint4 th = make_uint4(kNoInstance, 0u, kNoInstance, 0u);
+                        if (SLOTS == 2) {
+                            th = __ldg(reinterpret_cast<const uint4*>(ray_hints) + (size_t)bit * px_total + pix);
+                        } else {
+                            const uint2 t1 = __ldg(ray_hints + (size_t)bit * px_total + pix);
+                            th.x = t1.x, th.y = t1.y;
+                        }
+                        if (a.count_temporal) atomicAdd(&a.stats->detail[24], 1ull), atomicAdd(&a.stats->detail[25], th.x < n_inst ? 1ull : 0ull);
+                        // hints name instances by their index in the host's array, which survives TLAS rebuilds and refits
+                        own_inst = th.x < n_inst ? __ldg(a.inst_leaf + th.x) : kNoInstance;
+#pragma unroll
+                        for (int k = 0; k < SLOTS; k++) {
+                            const uint32_t hin = k ? th.z : th.x, ht = k ? th.w : th.y;
+                            if (!pending || hin >= n_inst) continue;
+                            const uint32_t hi = k ? __ldg(a.inst_leaf + hin) : own_inst;
+                            const float4 bhi = __ldg(a.scene.inst_boxes + 2 * (size_t)hi + 1);
+                            if (ht >= __float_as_uint(bhi.w)) continue; // not a triangle of that instance's BLAS
+                            const InstanceRec* rec = a.scene.instances + hi;
+                            const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1), r2 = __ldg(&rec->r2);
+                            const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&rec->nodes));
+                            const WideTri* tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                            const float3 o = xform_point(r0, r1, r2, O), d = xform_dir(r0, r1, r2, dir);
+                            const TriData q = load_tri(tris + ht);
+                            float tt, bu, bv;
+                            if (tri_test<false>(q, o, d, cross3_rn(o, d), 0.001f, tMaxRay, tt, bu, bv)) {
+                                ws.mask[lane * kSmemMaskWords + (bit >> 5)] |= 1u << (bit & 31u);
+                                pending = false;
+                                if (a.count_temporal) atomicAdd(&a.stats->detail[26], 1ull);
+                            }
+                        }
+                    }
+                    hint_own = own_inst;
+                }
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, pending);
+                n_fired += __popc(__ballot_sync(0xFFFFFFFFu, fired));
+                n_settled += __popc(__ballot_sync(0xFFFFFFFFu, fired && !pending));
+                if (m) {
+                    const uint32_t hint = a.hints ? __ldg(a.hints + hint_base + (uint32_t)light) : kNoInstance;
+                    if (pending) { // first candidate of the traversal: the ray's own last occluder instance, else the tile's hint
+                        const int pos = q_count + __popc(m & lt_mask);
+                        ws.q0[pos] = make_float4(O.x, O.y, O.z, tMaxRay);
+                        ws.q1[pos] = make_float4(dir.x, dir.y, dir.z, __uint_as_float((uint32_t)lane | (bit << 8)));
+                        ws.aux[pos] = hint_own != kNoInstance ? hint_own : hint;
+                    }
+                    q_count += __popc(m);
+                }
+                sample++;
+                __syncwarp();
+            }
+            if (q_count == 0) break; // nothing queued, nothing left to produce
+
+            // ---- drain one batch of unsettled rays: tile hint first, then the TLAS root; remember the occluder found ----
+            const int n = min(q_count, 32);
+            q_count -= n;
+            if (lane < n) {
+                const float4 i0 = ws.q0[q_count + lane], i1 = ws.q1[q_count + lane];
+                uint32_t aux = ws.aux[q_count + lane];
+                const uint32_t meta = __float_as_uint(i1.w), owner = meta & 31u, bit = meta >> 8;
+                HitInfo h;
+                h.inst = kNoInstance;
+                h.slot = 0u;
+                const bool hit = trace_ray<false, false, false, ONE_VISIT>(a.scene, f3(i0.x, i0.y, i0.z), f3(i1.x, i1.y, i1.z), 0.001f, i0.w, &h,
+                                                                           nullptr, stack, &aux, 1, aux != kNoInstance ? 1 : -1,
+                                                                           aux != kNoInstance);
+                if (hit) atomicOr(&ws.mask[owner * kSmemMaskWords + (bit >> 5)], 1u << (bit & 31u));
+                if (a.count_temporal) atomicAdd(&a.stats->detail[27], 1ull), atomicAdd(&a.stats->detail[28], hit ? 1ull : 0ull);
+                const uint32_t ox = bx * 8u + (owner & 7u), orow = by * 4u + (owner >> 3);
+                const size_t opix = (size_t)band_row(fc, a.rows, band, orow) * fc.width + ox;
+                if (SLOTS == 2) {
+                    uint4* slot = reinterpret_cast<uint4*>(ray_hints) + (size_t)bit * px_total + opix;
+                    if (hit) { // the new occluder in front, the previous one behind it
+                        const uint4 old = *slot;
+                        *slot = make_uint4(__ldg(a.inst_order + h.inst), h.slot, old.x, old.y);
+                    } else {
+                        *slot = make_uint4(kNoInstance, 0u, kNoInstance, 0u); // unoccluded: nothing to try next frame
+                    }
+                } else {
+                    ray_hints[(size_t)bit * px_total + opix] = hit ? make_uint2(__ldg(a.inst_order + h.inst), h.slot) : make_uint2(kNoInstance, 0u);
+                }
+            }
+            __syncwarp();
+        }
+        if (in_image)
+            for (uint32_t w = 0; w < a.shadow_words; w++) a.shadow_mask[pix * a.shadow_words + w] = ws.mask[lane * kSmemMaskWords + w];
+        if (lane == 0 && n_fired) { // 64 counter pairs, 128 bytes apart
+            unsigned long long* cnt = a.temporal_counters + 16u * (t & 63u);
+            atomicAdd(cnt, (unsigned long long)n_fired);
+            atomicAdd(cnt + 1, (unsigned long long)n_settled);
+        }
+        __syncwarp();
+    }
+}
+
 __global__ void k_pow22_table(float* __restrict__ t) { t[threadIdx.x] = powf((float)threadIdx.x / 255.0f, 2.2f); } // light.frag:172
 
 } // namespace
@@ -578,9 +792,23 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
         }
         if (any_shadow) {
             if (a2.hints && (e = launch_hints(shadow_stream)) != cudaSuccess) return e;
-            e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter, shadow_stream)
-                           : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter, shadow_stream)
-                                        : launch(k_light_rays_persistent<true, 6, 0>, args.tile_counter, shadow_stream);
+            if (args.ray_hints && args.shadow_words <= 8) { // per-ray temporal occluder hints
+                auto launch_t = [&](auto kern, size_t smem_t) -> cudaError_t {
+                    int per_sm = 0;
+                    cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem_t);
+                    if (e3 != cudaSuccess) return e3;
+                    kern<<<min((uint32_t)(sms * max(per_sm, 1)), (n_tiles + 3) / 4), 128, smem_t, shadow_stream>>>(
+                        a2, args.tile_counter, tx, ty, n_tiles, args.ray_hints, args.n_instances);
+                    ++*launches;
+                    return cudaGetLastError();
+                };
+                e = args.shadow_words <= 2 ? launch_t(k_shadow_rays_temporal<true, 6, 2, 2>, 4 * sizeof(ShadowQueue<2>))
+                                           : launch_t(k_shadow_rays_temporal<true, 6, 1, 8>, 4 * sizeof(ShadowQueue<8>));
+            } else {
+                e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter, shadow_stream)
+                               : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter, shadow_stream)
+                                            : launch(k_light_rays_persistent<true, 6, 0>, args.tile_counter, shadow_stream);
+            }
             if (e != cudaSuccess) return e;
         }
         if (any_ao) {

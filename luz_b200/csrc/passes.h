@@ -31,6 +31,13 @@ struct LightArgs {
     uint32_t* hints;                         // occluder hints [tile][light] of the shadow rays (nullptr: none), light_pass.cu
     uint32_t hint_sx, hint_sy;               // a hint tile is (1 << hint_sx) x (1 << hint_sy) pixels: 16 x 8 or 8 x 4
     uint32_t* tile_counter;                  // work counter of the persistent ray kernel (reset per launch)
+    uint2* ray_hints;                        // per-ray temporal occluder hints [shadow bit][pixel][slots] = (instance, triangle): two
+                                             // slots per ray while shadow_words <= 2, one beyond; nullptr: off
+    uint32_t n_instances;                    // instances of the current TLAS (bounds of the hints)
+    const uint32_t* inst_order;              // leaf position -> index in the host's instance array (tlas.prim_order)
+    const uint32_t* inst_leaf;               // index in the host's instance array -> leaf position
+    unsigned long long* temporal_counters;   // 64 x {shadow rays fired, settled by their temporal hints}, 128 B apart
+    uint32_t count_temporal;                 // LUZRT_TEMPORAL_COUNT=1: count hint tests / hits / queued rays in stats->detail[24..28]
     const ShadowMapRec* shadow_maps;         // per light, scene order (read only when fc.shadow_type == LUZW_SHADOW_MAP)
     const float* pow22;                      // 256 floats: (c / 255)^2.2 (launch_pow22_table)
     uint32_t exact_math;                     // 1: the bit-faithful shading kernel (LUZRT_DEBUG_EXACT_MATH)

@@ -16,6 +16,7 @@ struct HitInfo {
     float t;
     uint32_t inst; // index into the TLAS-ordered instance array
     uint32_t prim; // original triangle index inside the BLAS
+    uint32_t slot; // any-hit calls: index of the triangle that was hit in its BLAS's leaf-order triangle array
     float bu, bv;  // barycentric weights of v0, v1
     // input of trace_ray<.., FACE_CULL = true>: +1 / -1 = the sign s_view of the rasteriser view being emulated; a
     // triangle is kept iff s_view * sign(det instance) * dot(d, (v1 - v0) x (v2 - v0)) > 0 (shadow_map.cu)
@@ -487,7 +488,10 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
                         if (!(face_sign * dot3(d, n) > 0.0f)) continue;
                     }
                     if (!CLOSEST) {
-                        if (hit) hit->inst = cur_inst;
+                        if (hit) {
+                            hit->inst = cur_inst;
+                            hit->slot = prim;
+                        }
                         return true;
                     }
                     tmax = t;

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libluzrt.so")
 IMG_LIGHT, IMG_HISTORY, SHADOW_MASK, AO_MASK, STATS = 0, 1, 2, 3, 4
 GBUF_ALBEDO, GBUF_NORMAL, GBUF_MATERIAL, GBUF_EMISSION, GBUF_DEPTH, IMG_COMPOSE, TIMINGS = 5, 6, 7, 8, 9, 10, 11
 STATS_DETAIL = 12
-DEBUG_MASKS, DEBUG_STATS, DEBUG_NO_HINTS, DEBUG_EXACT_MATH = 1, 2, 4, 8
+DEBUG_MASKS, DEBUG_STATS, DEBUG_NO_HINTS, DEBUG_EXACT_MATH, DEBUG_NO_TEMPORAL = 1, 2, 4, 8, 16
 
 EXPORTS = [
     "luzrt_create", "luzrt_destroy", "luzrt_last_error", "luzrt_version", "luzrt_comm_unique_id",

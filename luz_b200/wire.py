@@ -59,7 +59,8 @@ class Stats(C.Structure):  # luzrt_stats
 
 class Timings(C.Structure):  # luzrt_timings
     _fields_ = [("tlas_ms", F), ("gbuffer_ms", F), ("light_ms", F), ("taa_ms", F), ("gather_ms", F),
-                ("compose_ms", F), ("volumetric_ms", F), ("shadow_map_ms", F), ("light_rays_ms", F)]
+                ("compose_ms", F), ("volumetric_ms", F), ("shadow_map_ms", F), ("light_rays_ms", F),
+                ("temporal_settled", F), ("temporal_on", F)]
 
 
 assert C.sizeof(LightBlock) == 480

@@ -52,6 +52,9 @@ def run_light(rt, sc, gb, frame, bn, extra=None):
     rt.light_pass(frame)
     assert np.array_equal(rt.read(R.SHADOW_MASK), sm) and np.array_equal(rt.read(R.AO_MASK), am)
     relaxed = rt.read(R.IMG_LIGHT)
+    rt.light_pass(frame)  # once more: the shadow rays now carry the occluders the pass above found (temporal hints, warm)
+    assert np.array_equal(rt.read(R.SHADOW_MASK), sm) and np.array_equal(rt.read(R.AO_MASK), am)
+    assert np.array_equal(rt.read(R.IMG_LIGHT), relaxed, equal_nan=True)
     assert np.array_equal(np.isnan(relaxed), np.isnan(out))
     fin = np.isfinite(out).all(axis=-1) & np.isfinite(relaxed).all(axis=-1)
     if fin.any():
@@ -430,6 +433,60 @@ def test_shadow_hints_do_not_change_visibility(rt_factory):
         st_plain = rt.read(R.STATS)
         assert st_hint.rays == st_plain.rays and st_hint.rays_occluded == st_plain.rays_occluded
         rt.close()
+
+
+def test_temporal_hints_do_not_change_visibility(rt_factory):
+    """Per-ray temporal occluder hints (k_shadow_rays_temporal, light_pass.cu): every shadow ray first tries the triangle
+    that occluded the same ray last frame.  The hint array is never invalidated -- whatever it holds, an entry is bounds
+    checked and then only decides which triangle is tried first -- so the bits must equal those without hints
+    (LUZRT_DEBUG_NO_TEMPORAL) on the first frame, on later frames of the same view, after the camera and the lights have
+    moved, after the TLAS has been refit and rebuilt under it with the instances in another order and fewer of them, with
+    several samples per light, and the image must follow."""
+    w, h = 320, 180
+    bn = S.blue_noise()
+    rt = rt_factory()
+    rt.resize(w, h)
+    rt.set_blue_noise(bn)
+
+    def frame_pair(sc, frame):
+        out = []
+        for flags in (R.DEBUG_NO_TEMPORAL, 0, 0):  # reference, hints cold or stale, hints warm
+            rt.set_debug(flags)
+            rt.light_pass(frame)
+            out.append((rt.read(R.SHADOW_MASK), rt.read(R.AO_MASK), rt.read(R.IMG_LIGHT)))
+        for got in out[1:]:
+            assert np.array_equal(got[0], out[0][0]) and np.array_equal(got[1], out[0][1])
+            assert np.array_equal(got[2], out[0][2], equal_nan=True)
+        return int(np.unpackbits(out[0][0].view(np.uint8)).sum())
+
+    occluded = 0
+    # 1 and 3 samples per light: <= 64 shadow rays per pixel, two hint slots per ray; 20 samples: 80 rays, the one-slot form
+    for samples, eyes in ((1, ((7, 3.0, 9), (7.05, 3.0, 9.02), (-6, 5.0, 4))), (3, ((7, 3.0, 9), (2, 8.0, 2))), (20, ((7, 3.0, 9),))):
+        for k, eye in enumerate(eyes):
+            sc = S.synthetic_scene(w, h, grid=5, n_lights=4, light_samples=samples, ao_samples=2, eye=eye)
+            blas, inst = S.make_rt_scene(rt, sc)
+            rt.set_scene(sc["scene"])
+            rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+            for frame in (3, 4, 131):
+                occluded += frame_pair(sc, frame)
+            # the same view over a TLAS whose instances moved (refit), then fewer instances in reverse order (rebuild)
+            moved = [(m, (np.array(mat).reshape(4, 4) + np.array([[0, 0, 0, 0]] * 3 + [[0.4, 0.0, -0.3, 0]], np.float32)).reshape(16), ci)
+                     for (m, mat, ci) in sc["instances"]]
+            inst2 = rt.make_instances([blas[m] for (m, _, _) in moved], [mat for (_, mat, _) in moved], [ci for (_, _, ci) in moved])
+            rt.tlas_build(inst2, len(moved), 1)
+            occluded += frame_pair(sc, 5)
+            fewer = moved[::-1][: len(moved) - 7]
+            inst3 = rt.make_instances([blas[m] for (m, _, _) in fewer], [mat for (_, mat, _) in fewer], [ci for (_, _, ci) in fewer])
+            rt.tlas_build(inst3, len(fewer), 0)
+            occluded += frame_pair(sc, 6)
+    assert occluded > 50000  # the scenes do have shadows
+    # another resolution on the same ctx: the hint array is reallocated, not reused out of bounds
+    rt.resize(w // 2, h // 2)
+    sc = S.synthetic_scene(w // 2, h // 2, grid=3, n_lights=2, light_samples=1, ao_samples=0)
+    S.make_rt_scene(rt, sc)
+    rt.set_scene(sc["scene"])
+    rt.gbuffer_pass(sc["models"], len(sc["instances"]))
+    frame_pair(sc, 9)
 
 
 def test_tlas_refit_matches_rebuild(rt_factory):
