@@ -498,6 +498,123 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_light_rays_persistent(const
     }
 }
 
+// ---- AO rays, candidate-major ----------------------------------------------------------------------------------------------
+// The AO rays of a pixel leave one origin and visit the same short candidate list (usually one instance).  Looping
+// candidates outside and samples inside loads the instance record and transforms the origin once per pixel and
+// candidate instead of once per ray, and the inner traversal is trace_blas_any -- one BLAS, no TLAS / candidate state
+// machine, fewer live registers, fewer phases for the lanes of a warp to disagree on.  The per-ray arithmetic (world
+// direction, world-box pre-test, object-space direction, node and triangle tests) is what trace_ray's candidate mode
+// does, so the bits are the same.  Pixels whose list overflowed (n_cand < 0) descend from the TLAS root with trace_ray.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_ao_rays_persistent(const LightArgs a, uint32_t* __restrict__ tile_counter,
+                                                                        const uint32_t tiles_x, const uint32_t tiles_y,
+                                                                        const uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(smem_raw) + warp * (kMaxCand * 32) + lane; // candidate lists [k][lane]
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const int n_samples = fc.ao_num_samples; // <= 64 (two mask words in registers); more samples take the generic kernel
+    uint2 stack[LUZ_STACK_SIZE];
+
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t bx = t % tiles_x, by = (t / tiles_x) % tiles_y, band = t / (tiles_x * tiles_y);
+        const uint32_t x = bx * 8u + (lane & 7), r = by * 4u + (lane >> 3);
+        const bool in_image = x < fc.width && r < a.rows.rows;
+        const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
+        const size_t pix = (size_t)y * fc.width + x;
+        float3 N = f3(0.0f, 0.0f, 0.0f);
+        float depth = 1.0f;
+        uchar4 bn8 = make_uchar4(0, 0, 0, 0);
+        if (in_image) {
+            const float4 n4 = __ldg(a.normal + pix);
+            N = f3(n4.x, n4.y, n4.z);
+            depth = __ldg(a.depth + pix);
+            bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+        }
+        const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
+        uint32_t occl0 = 0u, occl1 = 0u; // bit i: AO ray i occluded
+        if (lit) { // TraceAORays (light.frag:111-135)
+            const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+            const float3 fragPos = depth_to_world(fc, u, v, depth);
+            const float camDist = length3(fragPos - camPos);
+            const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+            const float3 O = fragPos + N * (camDist * 0.01f);
+            const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+            const float3 B = cross3(N, T);
+            const float tMinRay = fc.ao_min, tMaxRay = fc.ao_max;
+            int n_cand = -1; // < 0: rays descend from the TLAS root
+            if (n_samples >= kMinCandSamples) {
+                const float m = fabsf(tMaxRay) * 1.001f;
+                if (LUZ_AO_HEMISPHERE && tMinRay >= 0.0f && tMaxRay >= 0.0f) {
+                    float3 lo, hi;
+                    hemisphere_box(O, T, B, N, m, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                    n_cand = collect_instances<false>(a.scene, lo, hi, s_cand, 32, kMaxCand, stack, nullptr);
+                    if (n_cand > 0) n_cand = filter_candidates<false>(a.scene, O, T, B, N, m, s_cand, 32, n_cand, nullptr);
+                } else {
+                    const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + N.x * N.x) + 1e-6f,
+                                          m * sqrtf(T.y * T.y + B.y * B.y + N.y * N.y) + 1e-6f,
+                                          m * sqrtf(T.z * T.z + B.z * B.z + N.z * N.z) + 1e-6f);
+                    n_cand = collect_instances<false>(a.scene, O - ext, O + ext, s_cand, 32, kMaxCand, stack, nullptr);
+                }
+            }
+            const bool o_ok = O.x == O.x && O.y == O.y && O.z == O.z && tMinRay == tMinRay && tMaxRay == tMaxRay;
+            auto ao_dir = [&](const int i) -> float3 { // HemisphereSample (light.frag:63-69)
+                const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod);
+                const float rr = rg_sqrt(rng.x);
+                float sn, cs;
+                rg_sincos(6.283f * rng.y, &sn, &cs);
+                return rg_combine(T, rr * cs, B, rr * sn, N, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
+            };
+            if (n_cand < 0) {
+                for (int i = 0; i < n_samples; i++)
+                    if (trace_ray<false, false, false, true>(a.scene, O, ao_dir(i), tMinRay, tMaxRay, nullptr, nullptr, stack)) {
+                        if (i < 32) occl0 |= 1u << i; else occl1 |= 1u << (i - 32);
+                    }
+            } else if (o_ok) {
+                for (int c = 0; c < n_cand; c++) {
+                    const uint32_t id = s_cand[c * 32];
+                    const InstanceRec* rec = a.scene.instances + id;
+                    const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1), r2 = __ldg(&rec->r2);
+                    const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&rec->nodes));
+                    const WideNode* nodes = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+                    const WideTri* tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+                    const float4 blo = __ldg(a.scene.inst_boxes + 2 * id), bhi = __ldg(a.scene.inst_boxes + 2 * id + 1);
+                    const float3 o = xform_point(r0, r1, r2, O);
+                    const bool oo_ok = o.x == o.x && o.y == o.y && o.z == o.z;
+                    for (int i = 0; i < n_samples; i++) {
+                        if ((i < 32 ? occl0 >> i : occl1 >> (i - 32)) & 1u) continue; // an earlier candidate occludes it
+                        const float3 wd = ao_dir(i);
+                        if (!(wd.x == wd.x && wd.y == wd.y && wd.z == wd.z) || (wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f)) continue;
+                        // the ray segment against the instance's world box (trace_ray's candidate pre-test)
+                        const float3 widir = f3(safe_rcp(wd.x), safe_rcp(wd.y), safe_rcp(wd.z));
+                        const float tx0 = (blo.x - O.x) * widir.x, tx1 = (bhi.x - O.x) * widir.x;
+                        const float ty0 = (blo.y - O.y) * widir.y, ty1 = (bhi.y - O.y) * widir.y;
+                        const float tz0 = (blo.z - O.z) * widir.z, tz1 = (bhi.z - O.z) * widir.z;
+                        const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tMinRay));
+                        const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tMaxRay));
+                        if (!(tn - tf <= 2e-6f * fmaxf(fabsf(tn), fabsf(tf)))) continue;
+                        const float3 d = xform_dir(r0, r1, r2, wd);
+                        if (!oo_ok || !(d.x == d.x && d.y == d.y && d.z == d.z) || (d.x == 0.0f && d.y == 0.0f && d.z == 0.0f)) continue;
+                        if (trace_blas_any<true>(nodes, tris, o, d, tMinRay, tMaxRay, stack)) {
+                            if (i < 32) occl0 |= 1u << i; else occl1 |= 1u << (i - 32);
+                        }
+                    }
+                }
+            }
+        }
+        if (in_image) { // every pixel of the tile gets its words (zero for background and unoccluded pixels): no clear pass
+            a.ao_mask[pix * a.ao_words] = occl0;
+            if (a.ao_words > 1) a.ao_mask[pix * a.ao_words + 1] = occl1;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- shadow rays with per-ray temporal occluder hints ---------------------------------------------------------------------
 // 87 % of C3's shadow rays are occluded, and the ray a pixel fires towards a light this frame is -- up to the TAA jitter
 // and one step of the blue-noise sequence -- the ray it fired last frame.  The triangle that occluded it then very
@@ -812,9 +929,20 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
             if (e != cudaSuccess) return e;
         }
         if (any_ao) {
-            e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 1>, args.tile_counter + 1, stream)
-                           : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 1>, args.tile_counter + 1, stream)
-                                        : launch(k_light_rays_persistent<true, 6, 1>, args.tile_counter + 1, stream);
+            static const bool ao_generic_env = [] { // LUZRT_AO_KERNEL=generic: the per-ray trace_ray loop for AO too (A/B runs)
+                const char* e2 = getenv("LUZRT_AO_KERNEL");
+                return e2 && e2[0] == 'g';
+            }();
+            static const int ao_minb = [] { // resident CTAs per SM the AO kernel is compiled for (LUZRT_AO_MINB: tuning runs)
+                const char* e2 = getenv("LUZRT_AO_MINB");
+                return e2 ? atoi(e2) : 5;
+            }();
+            if (!ao_generic_env && args.ao_words <= 2)
+                e = ao_minb == 4 ? launch(k_ao_rays_persistent<4>, args.tile_counter + 1, stream)
+                                 : ao_minb == 6 ? launch(k_ao_rays_persistent<6>, args.tile_counter + 1, stream)
+                                                : launch(k_ao_rays_persistent<5>, args.tile_counter + 1, stream);
+            else
+                e = launch(k_light_rays_persistent<true, 6, 1>, args.tile_counter + 1, stream);
             if (e != cudaSuccess) return e;
         }
         if (fork) {

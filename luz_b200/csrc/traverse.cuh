@@ -562,4 +562,46 @@ __device__ __forceinline__ bool trace_ray(const TraceScene& sc, const float3 wo,
     return found;
 }
 
+// Any-hit against ONE BLAS, for callers that already hold the object-space ray (the AO kernel: all rays of a pixel share
+// their origin and their short candidate list, so the instance record is loaded and the origin transformed once per
+// pixel and candidate, and the loop below carries no TLAS / candidate state).  Same node test, leaf expansion and
+// triangle test as trace_ray, same arithmetic on the same operands.  The caller has checked the ray for NaNs and a
+// null direction.  `stack` is LUZ_STACK_SIZE entries of caller storage.
+template <bool ONE_VISIT = true>
+__device__ __forceinline__ bool trace_blas_any(const WideNode* __restrict__ nodes, const WideTri* __restrict__ tris, const float3 o,
+                                               const float3 d, const float tmin, const float tmax, uint2* stack) {
+    const RaySpace rs = make_ray_space(o, d);
+    int sp = 0;
+    uint2 ngroup = make_uint2(0u, 0x80000000u); // root: slot 7 of a virtual parent with imask 0
+    uint2 tgroup = make_uint2(0u, 0u);
+    while (true) {
+        if (ngroup.y > 0x00FFFFFFu && tgroup.y == 0u) {
+            const uint32_t hits = ngroup.y;
+            const uint32_t imask = hits & 0xFFu;
+            const int bit = 31 - __clz(hits);
+            ngroup.y &= ~(1u << bit);
+            if (ngroup.y > 0x00FFFFFFu) stack[sp++] = ngroup;
+            const int slot = bit - 24;
+            const uint32_t rel = __popc(imask & ~(0xFFFFFFFFu << slot));
+            const WideNode* node = nodes + (ngroup.x + rel);
+            const uint4 hdr = __ldg(reinterpret_cast<const uint4*>(node));
+            const uint32_t slots = intersect_node(node, rs, tmin, tmax);
+            const uint32_t node_imask = hdr.x >> 24;
+            ngroup = make_uint2(hdr.x & 0x00FFFFFFu, ((slots & node_imask) << 24) | node_imask);
+            tgroup = make_uint2(hdr.y, leaf_bits(slots & ~node_imask, hdr.z, hdr.w));
+        }
+        while (tgroup.y != 0u) {
+            const int j = __ffs(tgroup.y) - 1;
+            tgroup.y &= tgroup.y - 1u;
+            const TriData q = load_tri(tris + tgroup.x + (uint32_t)j);
+            float t, bu, bv;
+            if (tri_test<false>(q, o, d, cross3_rn(o, d), tmin, tmax, t, bu, bv)) return true;
+        }
+        if (ngroup.y <= 0x00FFFFFFu) {
+            if (sp == 0) return false;
+            ngroup = stack[--sp];
+        }
+    }
+}
+
 } // namespace luz
