@@ -16,10 +16,10 @@ timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 : > $OUT/${TAG}_bench_other.json
 for c in c1 c2 c4 c5; do steps=10; [ $c = c5 ] && steps=5; timeout 500 python bench.py --config $c --no-cpu-baseline --steps $steps >> $OUT/${TAG}_bench_other.json 2>> $OUT/${TAG}_bench.err; done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_light|k_shadow_hints|k_taa|k_gbuffer|k_compose|refit|collapse" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_light|k_shadow|k_ao_rays|k_taa|k_gbuffer|k_compose|refit|collapse" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $OUT/${TAG}_launches_bench.log 2>&1
 i=0
-for spec in "k_shadow_hints:k_shadow_hints:2" "k_light_rays_persistent:k_light_rays_persistent_shadow:4" "k_light_rays_persistent:k_light_rays_persistent_ao:5" "k_light_shade:k_light_shade:2" "k_taa:k_taa:2"; do
+for spec in "k_shadow_hints:k_shadow_hints:4" "k_shadow_rays_temporal:k_shadow_rays_temporal:4" "k_ao_rays_persistent:k_ao_rays_persistent:4" "k_light_shade:k_light_shade:4" "k_taa:k_taa:4"; do
   IFS=: read k key skip <<< "$spec"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o $OUT/${TAG}_$key \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > $OUT/${TAG}_ncu_$key.log 2>&1
