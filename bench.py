@@ -451,7 +451,7 @@ def run_ours(args):
                 "l2_policy": ("inputs larger than L2 (G-buffer + 3 light buffers = %.0f MB > 126 MB)" if W * Hh * 80 > 126e6 else
                               "NOT flushed: G-buffer + 3 light buffers = %.0f MB fit the 126 MB L2 (reference-size config, "
                               "reported for parity, not a roofline claim)") % (W * Hh * 80 / 1e6)},
-            "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6]),
+            "kernels_ms": {"light": light_ms, "taa": taa_ms, "gather": float(mx[5]), "tlas": float(mx[6]) if animate else 0.0,
                            "light_rays": kavg["light_rays_ms"], "light_shade": kavg["light_ms"] - kavg["light_rays_ms"],
                            "light_per_rank": [round(v, 4) for v in per_rank_light],
                            "volumetric": kavg["volumetric_ms"] if args.volumetric else 0.0,
