@@ -161,6 +161,7 @@ struct luzrt_ctx {
     float* d_pow22 = nullptr; // (c / 255)^2.2, c = 0..255 (light.frag:172), for the shading kernels
     uint2* d_ray_hints = nullptr; // per-ray temporal occluder hints of the shadow rays, [shadow bit][pixel][slots] (light_pass.cu)
     size_t ray_hints_cap = 0;     // in uint2 elements
+    size_t ray_hints_refused = 0; // an allocation of this many elements failed: the pass runs without hints
     // the hints pay when last frame's occluders still occlude (static or slowly changing views) and cost a few per cent
     // when they do not (every instance moving every frame): the kernel counts how many rays they settle, the counters
     // come back asynchronously, and the pass uses the hints while the settled fraction stays above a threshold; while it
@@ -1280,11 +1281,16 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
                 if (c->d_ray_hints) cudaFree(c->d_ray_hints);
                 c->d_ray_hints = nullptr;
                 c->ray_hints_cap = 0;
-                if (cudaMalloc(&c->d_ray_hints, need * sizeof(uint2)) != cudaSuccess) return fail(c, LUZRT_E_NOMEM, "ray hints: %zu bytes", need * sizeof(uint2));
-                c->ray_hints_cap = need;
-                CU(c, cudaMemsetAsync(c->d_ray_hints, 0xFF, need * sizeof(uint2), c->stream));
+                if (c->ray_hints_refused != need && cudaMalloc(&c->d_ray_hints, need * sizeof(uint2)) == cudaSuccess) {
+                    c->ray_hints_cap = need;
+                    CU(c, cudaMemsetAsync(c->d_ray_hints, 0xFF, need * sizeof(uint2), c->stream));
+                } else { // no room for the hints: an optimisation the frame can do without (do not ask again for this size)
+                    cudaGetLastError();
+                    c->d_ray_hints = nullptr;
+                    c->ray_hints_refused = need;
+                }
             }
-            if (!c->d_temporal_cnt) {
+            if (c->d_ray_hints && !c->d_temporal_cnt) {
                 CU(c, cudaMalloc(&c->d_temporal_cnt, 64 * 16 * sizeof(unsigned long long)));
                 CU(c, cudaMallocHost(&c->h_temporal_cnt, 64 * 16 * sizeof(unsigned long long)));
                 CU(c, cudaEventCreateWithFlags(&c->ev_temporal, cudaEventDisableTiming));
@@ -1306,7 +1312,7 @@ int luzrt_light_pass(luzrt_ctx* c, uint32_t frame) {
             }();
             c->temporal_frame++;
             const bool probe = (c->temporal_frame & 31u) < 2u; // two frames out of 32
-            if (c->temporal_use || probe || !adaptive_env) {
+            if (c->d_ray_hints && (c->temporal_use || probe || !adaptive_env)) {
                 a.ray_hints = c->d_ray_hints;
                 a.temporal_counters = c->d_temporal_cnt;
             }
