@@ -615,6 +615,192 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) k_ao_rays_persistent(const Li
     }
 }
 
+// ---- AO rays, (pixel, candidate) pairs compacted over the warp ---------------------------------------------------------------
+// 71 % of C3's pixels have an empty candidate list; in the kernel above their lanes idle through the candidate and sample
+// loops of the 9 that do not (ncu: 8.8 active lanes in the node test, 2.6 in the triangle test).  Here the per-pixel part
+// (G-buffer load, box query, filter) stays one pixel per lane, but what it produces -- one work item per (pixel,
+// candidate instance), each worth ao_num_samples rays against ONE BLAS -- goes into a per-warp ring in shared memory
+// (ballot + prefix popcount) and is executed 32 items at a time, one per lane, whichever tile they came from.  An item
+// carries what its rays need (origin, normal, blue-noise texel, pixel, instance: 36 bytes) and is worth ~16 rays, so the
+// queue traffic that sank the all-rays experiment (profiles/r2_ray_queue_experiment.md) is amortised 16 times.  The
+// occlusion bits of a pixel's items are OR-ed into its mask word with atomicOr (the owner lane stored the zero word
+// before, ordered by __syncwarp); an item no ray of which is occluded -- most -- touches nothing.  Bits: OR over the
+// candidates of the per-candidate any-hit, as above (the "already occluded by an earlier candidate" skip is lost between
+// items in flight together; it only saved work).
+constexpr int kAoQueueCap = 64; // < 32 queued before a push round, <= 32 pushed by it
+struct __align__(16) AoPairQueue { // one per warp
+    float4 qa[kAoQueueCap];        // O.xyz, pixel index
+    float4 qb[kAoQueueCap];        // N.xyz, instance
+    uint32_t qc[kAoQueueCap];      // blue-noise texel: r | g << 8
+    uint32_t cand[kMaxCand * 32];  // candidate lists [k][lane]
+    float4 ra[kAoQueueCap];        // a ray: object-space origin, instance
+    float4 rb[kAoQueueCap];        // object-space direction, pixel | sample << 26
+};
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) k_ao_rays_compact(const LightArgs a, uint32_t* __restrict__ tile_counter,
+                                                                     const uint32_t tiles_x, const uint32_t tiles_y,
+                                                                     const uint32_t n_tiles) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const FrameConst& fc = a.fc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    AoPairQueue& ws = reinterpret_cast<AoPairQueue*>(smem_raw)[warp];
+    uint32_t* s_cand = ws.cand + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const float3 camPos = f3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+    const int n_samples = fc.ao_num_samples; // <= 64 (two mask words)
+    const float tMinRay = fc.ao_min, tMaxRay = fc.ao_max;
+    uint2 stack[LUZ_STACK_SIZE];
+    uint32_t q_head = 0, q_count = 0, r_head = 0, r_count = 0; // warp-uniform
+
+    auto sample_dir = [&](const float3& T, const float3& B, const float3& N, const float bn_r, const float bn_g, const int i) -> float3 {
+        const float2 rng = blue_noise_sample(bn_r, bn_g, i, fc.frame_mod); // HemisphereSample (light.frag:63-69)
+        const float rr = rg_sqrt(rng.x);
+        float sn, cs;
+        rg_sincos(6.283f * rng.y, &sn, &cs);
+        return rg_combine(T, rr * cs, B, rr * sn, N, rg_sqrt(fmaxf(0.0f, 1.0f - rng.x)));
+    };
+    // rays that passed the world-box pre-test: traced 32 at a time, whichever item they came from
+    auto trace_rays = [&](const uint32_t n) {
+        if ((uint32_t)lane < n) {
+            const uint32_t e = (r_head + (uint32_t)lane) & (kAoQueueCap - 1);
+            const float4 ra = ws.ra[e], rb = ws.rb[e];
+            const uint32_t id = __float_as_uint(ra.w), meta = __float_as_uint(rb.w);
+            const uint4 ptrs = __ldg(reinterpret_cast<const uint4*>(&a.scene.instances[id].nodes));
+            const WideNode* nodes = reinterpret_cast<const WideNode*>(((unsigned long long)ptrs.y << 32) | ptrs.x);
+            const WideTri* tris = reinterpret_cast<const WideTri*>(((unsigned long long)ptrs.w << 32) | ptrs.z);
+            if (trace_blas_any<true>(nodes, tris, f3(ra.x, ra.y, ra.z), f3(rb.x, rb.y, rb.z), tMinRay, tMaxRay, stack)) {
+                const uint32_t bit = meta >> 26;
+                atomicOr(a.ao_mask + (size_t)(meta & 0x3FFFFFFu) * a.ao_words + (bit >> 5), 1u << (bit & 31u));
+            }
+        }
+        __syncwarp();
+        r_head = (r_head + n) & (kAoQueueCap - 1);
+        r_count -= n;
+    };
+    auto drain = [&](const uint32_t n) { // the n (<= 32) oldest items, one per lane: generate their rays
+        const bool have = (uint32_t)lane < n;
+        const uint32_t e = (q_head + (uint32_t)(have ? lane : 0)) & (kAoQueueCap - 1);
+        const float4 qa = ws.qa[e], qb = ws.qb[e];
+        const uint32_t bn = ws.qc[e], id = __float_as_uint(qb.w);
+        const uint32_t pix = __float_as_uint(qa.w);
+        const float3 O = f3(qa.x, qa.y, qa.z), N = f3(qb.x, qb.y, qb.z);
+        const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+        const float3 B = cross3(N, T);
+        const float bn_r = (float)(bn & 255u) / 255.0f, bn_g = (float)(bn >> 8) / 255.0f;
+        const InstanceRec* rec = a.scene.instances + id;
+        const float4 r0 = __ldg(&rec->r0), r1 = __ldg(&rec->r1), r2 = __ldg(&rec->r2);
+        const float4 blo = __ldg(a.scene.inst_boxes + 2 * id), bhi = __ldg(a.scene.inst_boxes + 2 * id + 1);
+        const float3 o = xform_point(r0, r1, r2, O);
+        const bool oo_ok = have && o.x == o.x && o.y == o.y && o.z == o.z;
+        for (int i = 0; i < n_samples; i++) {
+            const float3 wd = sample_dir(T, B, N, bn_r, bn_g, i);
+            bool fire = oo_ok && (wd.x == wd.x && wd.y == wd.y && wd.z == wd.z) && !(wd.x == 0.0f && wd.y == 0.0f && wd.z == 0.0f);
+            // the ray segment against the instance's world box (trace_ray's candidate pre-test)
+            const float3 widir = f3(safe_rcp(wd.x), safe_rcp(wd.y), safe_rcp(wd.z));
+            const float tx0 = (blo.x - O.x) * widir.x, tx1 = (bhi.x - O.x) * widir.x;
+            const float ty0 = (blo.y - O.y) * widir.y, ty1 = (bhi.y - O.y) * widir.y;
+            const float tz0 = (blo.z - O.z) * widir.z, tz1 = (bhi.z - O.z) * widir.z;
+            const float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tMinRay));
+            const float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tMaxRay));
+            fire = fire && (tn - tf <= 2e-6f * fmaxf(fabsf(tn), fabsf(tf)));
+            const float3 d = xform_dir(r0, r1, r2, wd);
+            fire = fire && (d.x == d.x && d.y == d.y && d.z == d.z) && !(d.x == 0.0f && d.y == 0.0f && d.z == 0.0f);
+            const uint32_t bl = __ballot_sync(0xFFFFFFFFu, fire);
+            if (fire) {
+                const uint32_t k = (r_head + r_count + __popc(bl & lt_mask)) & (kAoQueueCap - 1);
+                ws.ra[k] = make_float4(o.x, o.y, o.z, __uint_as_float(id));
+                ws.rb[k] = make_float4(d.x, d.y, d.z, __uint_as_float(pix | ((uint32_t)i << 26)));
+            }
+            r_count += __popc(bl);
+            __syncwarp();
+            if (r_count >= 32) trace_rays(32);
+        }
+        q_head = (q_head + n) & (kAoQueueCap - 1);
+        q_count -= n;
+    };
+
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(tile_counter, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t bx = t % tiles_x, by = (t / tiles_x) % tiles_y, band = t / (tiles_x * tiles_y);
+        const uint32_t x = bx * 8u + (lane & 7), r = by * 4u + (lane >> 3);
+        const bool in_image = x < fc.width && r < a.rows.rows;
+        const uint32_t y = in_image ? band_row(fc, a.rows, band, r) : 0u;
+        const size_t pix = (size_t)y * fc.width + x;
+        float3 N = f3(0.0f, 0.0f, 0.0f);
+        float depth = 1.0f;
+        uchar4 bn8 = make_uchar4(0, 0, 0, 0);
+        if (in_image) {
+            const float4 n4 = __ldg(a.normal + pix);
+            N = f3(n4.x, n4.y, n4.z);
+            depth = __ldg(a.depth + pix);
+            bn8 = __ldg(a.blue_noise + (size_t)(y % fc.bn_h) * fc.bn_w + (x % fc.bn_w));
+        }
+        const bool lit = in_image && (length3(N) != 0.0f); // light.frag:178
+        uint32_t occl0 = 0u, occl1 = 0u; // bits found here (pixels whose list overflowed); the items add theirs later
+        int n_cand = 0;
+        float3 O = f3(0.0f, 0.0f, 0.0f);
+        if (lit) { // TraceAORays (light.frag:111-135)
+            const float u = ((float)x + 0.5f) / (float)fc.width, v = ((float)y + 0.5f) / (float)fc.height;
+            const float3 fragPos = depth_to_world(fc, u, v, depth);
+            const float camDist = length3(fragPos - camPos);
+            O = fragPos + N * (camDist * 0.01f);
+            const float3 T = fabsf(N.z) > 0.5f ? f3(0.0f, -N.z, N.y) : f3(-N.y, N.x, 0.0f);
+            const float3 B = cross3(N, T);
+            n_cand = -1; // < 0: rays descend from the TLAS root
+            if (n_samples >= kMinCandSamples) {
+                const float m = fabsf(tMaxRay) * 1.001f;
+                if (LUZ_AO_HEMISPHERE && tMinRay >= 0.0f && tMaxRay >= 0.0f) {
+                    float3 lo, hi;
+                    hemisphere_box(O, T, B, N, m, f3(2e-6f * fabsf(O.x) + 1e-6f, 2e-6f * fabsf(O.y) + 1e-6f, 2e-6f * fabsf(O.z) + 1e-6f), lo, hi);
+                    n_cand = collect_instances<false>(a.scene, lo, hi, s_cand, 32, kMaxCand, stack, nullptr);
+                    if (n_cand > 0) n_cand = filter_candidates<false>(a.scene, O, T, B, N, m, s_cand, 32, n_cand, nullptr);
+                } else {
+                    const float3 ext = f3(m * sqrtf(T.x * T.x + B.x * B.x + N.x * N.x) + 1e-6f,
+                                          m * sqrtf(T.y * T.y + B.y * B.y + N.y * N.y) + 1e-6f,
+                                          m * sqrtf(T.z * T.z + B.z * B.z + N.z * N.z) + 1e-6f);
+                    n_cand = collect_instances<false>(a.scene, O - ext, O + ext, s_cand, 32, kMaxCand, stack, nullptr);
+                }
+            }
+            const bool o_ok = O.x == O.x && O.y == O.y && O.z == O.z && tMinRay == tMinRay && tMaxRay == tMaxRay;
+            if (n_cand < 0) {
+                const float bn_r = (float)bn8.x / 255.0f, bn_g = (float)bn8.y / 255.0f;
+                for (int i = 0; i < n_samples; i++)
+                    if (trace_ray<false, false, false, true>(a.scene, O, sample_dir(T, B, N, bn_r, bn_g, i), tMinRay, tMaxRay, nullptr, nullptr, stack)) {
+                        if (i < 32) occl0 |= 1u << i; else occl1 |= 1u << (i - 32);
+                    }
+                n_cand = 0;
+            } else if (!o_ok) {
+                n_cand = 0;
+            }
+        }
+        if (in_image) { // every pixel of the tile gets its words: no clear pass
+            a.ao_mask[pix * a.ao_words] = occl0;
+            if (a.ao_words > 1) a.ao_mask[pix * a.ao_words + 1] = occl1;
+        }
+        __syncwarp(); // the words are stored before any item of this tile ORs into them
+        const int max_c = __reduce_max_sync(0xFFFFFFFFu, n_cand);
+        for (int c = 0; c < max_c; c++) {
+            const bool push = c < n_cand;
+            const uint32_t b = __ballot_sync(0xFFFFFFFFu, push);
+            if (push) {
+                const uint32_t e = (q_head + q_count + __popc(b & lt_mask)) & (kAoQueueCap - 1);
+                ws.qa[e] = make_float4(O.x, O.y, O.z, __uint_as_float((uint32_t)pix));
+                ws.qb[e] = make_float4(N.x, N.y, N.z, __uint_as_float(s_cand[c * 32]));
+                ws.qc[e] = (uint32_t)bn8.x | ((uint32_t)bn8.y << 8);
+            }
+            q_count += __popc(b);
+            __syncwarp();
+            if (q_count >= 32) drain(32);
+        }
+    }
+    if (q_count) drain(q_count);
+    if (r_count) trace_rays(r_count);
+}
+
 // ---- shadow rays with per-ray temporal occluder hints ---------------------------------------------------------------------
 // 87 % of C3's shadow rays are occluded, and the ray a pixel fires towards a light this frame is -- up to the TAA jitter
 // and one step of the blue-noise sequence -- the ray it fired last frame.  The triangle that occluded it then very
@@ -935,9 +1121,24 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
             }();
             static const int ao_minb = [] { // resident CTAs per SM the AO kernel is compiled for (LUZRT_AO_MINB: tuning runs)
                 const char* e2 = getenv("LUZRT_AO_MINB");
-                return e2 ? atoi(e2) : 5;
+                return e2 ? atoi(e2) : 0;
             }();
-            if (!ao_generic_env && args.ao_words <= 2)
+            static const bool ao_compact_env = [] { // LUZRT_AO_KERNEL=candidate: the kernel without item compaction (A/B runs)
+                const char* e2 = getenv("LUZRT_AO_KERNEL");
+                return !(e2 && e2[0] == 'c');
+            }();
+            if (!ao_generic_env && ao_compact_env && args.ao_words <= 2 && px <= 0x4000000ull) { // pixel | sample << 26 in a word
+                auto launch_c = [&](auto kern) -> cudaError_t {
+                    const size_t smem_c = 4 * sizeof(AoPairQueue);
+                    int per_sm = 0;
+                    cudaError_t e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem_c);
+                    if (e3 != cudaSuccess) return e3;
+                    kern<<<min((uint32_t)(sms * max(per_sm, 1)), (n_tiles + 3) / 4), 128, smem_c, stream>>>(a2, args.tile_counter + 1, tx, ty, n_tiles);
+                    ++*launches;
+                    return cudaGetLastError();
+                };
+                e = ao_minb == 4 ? launch_c(k_ao_rays_compact<4>) : ao_minb == 5 ? launch_c(k_ao_rays_compact<5>) : launch_c(k_ao_rays_compact<6>);
+            } else if (!ao_generic_env && args.ao_words <= 2)
                 e = ao_minb == 4 ? launch(k_ao_rays_persistent<4>, args.tile_counter + 1, stream)
                                  : ao_minb == 6 ? launch(k_ao_rays_persistent<6>, args.tile_counter + 1, stream)
                                                 : launch(k_ao_rays_persistent<5>, args.tile_counter + 1, stream);
