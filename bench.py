@@ -459,15 +459,15 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             # the dominant kernel (ray generation + any-hit traversal) against the memory level its working set lives in
-            "roofline": {"kernel": "k_shadow_hints + the ray kernels (k_shadow_rays_temporal, k_ao_rays_persistent: ray generation + "
+            "roofline": {"kernel": "k_shadow_hints + the ray kernels (k_shadow_rays_temporal, k_ao_rays_compact: ray generation + "
                                    "any-hit traversal, the dominant kernels), timed with CUDA events on the launch stream", "bound": "l2",
                          "achieved": (trav_bytes + rays_stream) / (rays_ms * 1e6), "peak": trav_peak, "unit": "GB/s",
                          "frac": (trav_bytes + rays_stream) / (rays_ms * 1e6) / trav_peak if trav_peak else None,
                          "traffic": (lambda a, b, c: (a + b + c) if None not in (a, b, c) else None)(
                              ncu_traffic(args, "k_shadow_rays_temporal", src_hash),
-                             ncu_traffic(args, "k_ao_rays_persistent", src_hash), ncu_traffic(args, "k_shadow_hints", src_hash)),
+                             ncu_traffic(args, "k_ao_rays_compact", src_hash), ncu_traffic(args, "k_shadow_hints", src_hash)),
                          "peak_source": "luzrt_probe_read_bandwidth, 32 MiB L2-resident buffer, measured in this run",
-                         "ncu": ncu_counters(args, ("k_shadow_rays_temporal", "k_ao_rays_persistent", "k_shadow_hints"), src_hash),
+                         "ncu": ncu_counters(args, ("k_shadow_rays_temporal", "k_ao_rays_compact", "k_shadow_hints"), src_hash),
                          "algorithmic_bytes": "SURVEY 8(d): per ray 80 B/node + 48 B/triangle + 64 B/instance (counted by the "
                                               "statistics variant of the same kernel on the same BVH and rays) + 20 B/px "
                                               "normal+depth in + 4 B/px per mask word out",

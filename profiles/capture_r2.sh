@@ -19,9 +19,14 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_light|k_shadow|k_ao_rays|k_taa|k_gbuffer|k_compose|refit|collapse" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > $OUT/${TAG}_launches_bench.log 2>&1
 i=0
-for spec in "k_shadow_hints:k_shadow_hints:4" "k_shadow_rays_temporal:k_shadow_rays_temporal:4" "k_ao_rays_persistent:k_ao_rays_persistent:4" "k_light_shade:k_light_shade:4" "k_taa:k_taa:4"; do
+for spec in "k_shadow_hints:k_shadow_hints:4" "k_shadow_rays_temporal:k_shadow_rays_temporal:4" "k_ao_rays_compact:k_ao_rays_compact:4" "k_light_shade:k_light_shade:4" "k_taa:k_taa:4"; do
   IFS=: read k key skip <<< "$spec"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o $OUT/${TAG}_$key \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-parity > $OUT/${TAG}_ncu_$key.log 2>&1
+done
+for tool in memcheck racecheck; do
+  timeout 800 compute-sanitizer --tool $tool --log-file $OUT/${TAG}_sanitizer_$tool.log python -m pytest tests/test_gpu_parity.py -m gpu -q -x \
+      -k "default_scene_file_settings or synthetic_multi_light or taa_parity or tlas_refit or empty_and_degenerate or gbuffer_pass_culls or shadow_hints or temporal" > $OUT/${TAG}_sanitizer_${tool}_pytest.log 2>&1
+  tail -1 $OUT/${TAG}_sanitizer_${tool}_pytest.log; tail -1 $OUT/${TAG}_sanitizer_$tool.log
 done
 tail -3 $OUT/${TAG}_pytest.log; tail -2 $OUT/${TAG}_pytest_exact_raygen.log; tail -1 $OUT/${TAG}_smoke.log; cut -c1-300 $OUT/${TAG}_bench.json
