@@ -1105,8 +1105,16 @@ cudaError_t launch_light_pass(cudaStream_t stream, const LightArgs& args, bool s
                     ++*launches;
                     return cudaGetLastError();
                 };
-                e = args.shadow_words <= 2 ? launch_t(k_shadow_rays_temporal<true, 6, 2, 2>, 4 * sizeof(ShadowQueue<2>))
-                                           : launch_t(k_shadow_rays_temporal<true, 6, 1, 8>, 4 * sizeof(ShadowQueue<8>));
+                static const int tminb = [] { // resident CTAs per SM (LUZRT_TEMPORAL_MINB: tuning runs)
+                    const char* e2 = getenv("LUZRT_TEMPORAL_MINB");
+                    return e2 ? atoi(e2) : 6;
+                }();
+                if (args.shadow_words <= 2)
+                    e = tminb == 5 ? launch_t(k_shadow_rays_temporal<true, 5, 2, 2>, 4 * sizeof(ShadowQueue<2>))
+                                   : tminb == 7 ? launch_t(k_shadow_rays_temporal<true, 7, 2, 2>, 4 * sizeof(ShadowQueue<2>))
+                                                : launch_t(k_shadow_rays_temporal<true, 6, 2, 2>, 4 * sizeof(ShadowQueue<2>));
+                else
+                    e = launch_t(k_shadow_rays_temporal<true, 6, 1, 8>, 4 * sizeof(ShadowQueue<8>));
             } else {
                 e = pminb == 5 ? launch(k_light_rays_persistent<true, 5, 0>, args.tile_counter, shadow_stream)
                                : pminb == 7 ? launch(k_light_rays_persistent<true, 7, 0>, args.tile_counter, shadow_stream)
